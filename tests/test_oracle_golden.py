@@ -1,0 +1,168 @@
+"""Pins the CPU oracle (oracle/) against fixtures produced by the reference itself
+(tests/golden/make_golden.py: reference CorrBlock / IterativeCorrBlock / RAFT-small on CPU).
+
+The reference ships no tests for this path; these fixtures are the pin.
+Tolerance: 1e-5 relative to max-abs for forward values (fp32 rounding of two different but
+equivalent evaluation orders; the product tolerance is 1e-4), 1e-4 for gradients.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import cotangent, load_golden, rel_err
+from oracle import oracle as orc
+
+FWD_TOL = 1e-5
+GRAD_TOL = 1e-4
+
+
+def _block(g, **kw):
+    B, C, H, W, L, r, _ = [int(v) for v in g["meta"]]
+    return orc.OracleCorrBlock(g["fmap1"], g["fmap2"], num_levels=L, radius=r, **kw), L, r
+
+
+@pytest.mark.parametrize("name", ["corrblock_odd", "corrblock_full_r4", "corrblock_small_r3",
+                                  "corrblock_edges", "corrblock_onehot"])
+def test_corrblock_forward_matches_reference(name):
+    g = load_golden(name)
+    blk, L, r = _block(g)
+    for i in range(L):
+        if f"pyr{i}" in g:
+            assert blk.corr_pyramid[i].shape == g[f"pyr{i}"].shape
+            assert rel_err(blk.corr_pyramid[i], g[f"pyr{i}"]) < FWD_TOL, f"pyramid level {i}"
+    out = blk(g["coords"])
+    assert out.shape == g["out"].shape and out.dtype == np.float32
+    assert rel_err(out, g["out"]) < FWD_TOL
+    # the direct pixel-space evaluation the CUDA kernels use differs only by coordinate ulps
+    assert rel_err(blk(g["coords"], roundtrip=False), g["out"]) < 2e-5
+
+
+def test_float_accumulation_mode_is_within_tolerance():
+    g = load_golden("corrblock_full_r4")
+    blk, _, _ = _block(g, acc64=False)
+    assert rel_err(blk(g["coords"]), g["out"]) < FWD_TOL
+
+
+@pytest.mark.parametrize("name", ["corrblock_odd", "corrblock_full_r4"])
+def test_corrblock_backward_matches_reference_autograd(name):
+    g = load_golden(name)
+    blk, _, _ = _block(g)
+    go = cotangent(g["meta"][6], g["out"].shape)
+    df1, df2, dco = blk.backward(g["coords"], go)
+    assert rel_err(df1, g["df1"]) < GRAD_TOL
+    assert rel_err(df2, g["df2"]) < GRAD_TOL
+    assert rel_err(dco, g["dcoords"]) < GRAD_TOL
+    assert np.abs(g["dcoords"]).max() > 1.0  # CorrBlock autograd gives real coords grads
+
+
+def test_known_answers():
+    """SURVEY 8c (i)-(iii)."""
+    g = load_golden("corrblock_onehot")
+    blk, L, r = _block(g)
+    rd = 2 * r + 1
+    out = blk(g["coords"])
+    # (ii) x-offset is the slow window index: query (x=9,y=5) sees the one-hot at dx=+1,dy=0 -> channel 17
+    assert list(np.nonzero(out[0, :rd * rd, 5, 9])[0]) == [(1 + r) * rd + r] and out[0, 17, 5, 9] == 1.0
+    assert list(np.nonzero(out[0, :rd * rd, 4, 10])[0]) == [r * rd + (1 + r)] and out[0, 13, 4, 10] == 1.0
+    # (i) integer coords: centre channel of level 0 is <F1[q],F2[q]>/sqrt(C)
+    g2 = load_golden("corrblock_full_r4")
+    blk2, L2, r2 = _block(g2)
+    B, C, H, W = g2["fmap1"].shape
+    ys, xs = np.meshgrid(np.arange(H), np.arange(W), indexing="ij")
+    grid = np.stack([xs, ys])[None].astype(np.float32)
+    centre = blk2(grid)[:, r2 * (2 * r2 + 1) + r2]
+    want = (g2["fmap1"].astype(np.float64) * g2["fmap2"]).sum(1) / np.sqrt(C)
+    assert rel_err(centre, want) < FWD_TOL
+    # (iii) far outside -> exact zeros at every level
+    assert not blk2(grid + 1000.0).any()
+
+
+def test_alternate_block_matches_both_reference_formulations():
+    """On-the-fly path (restating alt_cuda_corr's kernel) vs the reference's all-pairs CorrBlock and its
+    pure-torch IterativeCorrBlock on the same inputs (SURVEY 8c v: they agree to ~2.6e-5 abs)."""
+    g = load_golden("corrblock_full_r4")
+    it = load_golden("altcorr_iterative_r4")
+    B, C, H, W, L, r, _ = [int(v) for v in g["meta"]]
+    alt = orc.OracleAlternateCorrBlock(g["fmap1"], g["fmap2"], num_levels=L, radius=r)
+    assert len(alt.pyramid) == L + 1
+    out = alt(g["coords"])
+    assert out.shape == g["out"].shape
+    assert rel_err(out, it["out"]) < FWD_TOL
+    assert rel_err(out, g["out"]) < FWD_TOL
+
+
+def test_alt_backward_is_consistent_with_corrblock_autograd():
+    """alt_cuda_corr.backward (per level, unscaled) summed over levels with the pooled-feature chain rule
+    equals the all-pairs autograd gradient (SURVEY 8c vi).  Also: the reference kernel leaves
+    coords_grad zero, the oracle's true-gradient option reproduces CorrBlock's coords gradient."""
+    g = load_golden("corrblock_full_r4")
+    B, C, H, W, L, r, seed = [int(v) for v in g["meta"]]
+    rd = 2 * r + 1
+    go = cotangent(seed, g["out"].shape).reshape(B, L, rd * rd, H, W) / np.float32(np.sqrt(C))
+    alt = orc.OracleAlternateCorrBlock(g["fmap1"], g["fmap2"], num_levels=L, radius=r)
+    coords = g["coords"].transpose(0, 2, 3, 1)
+    f1 = np.ascontiguousarray(alt.pyramid[0][0].transpose(0, 2, 3, 1))
+    df1 = np.zeros_like(f1)
+    df2 = np.zeros((B, C, H, W), np.float32)
+    dco = np.zeros((B, H, W, 2), np.float32)
+    for i in range(L):
+        f2 = np.ascontiguousarray(alt.pyramid[i][1].transpose(0, 2, 3, 1))
+        ci = np.ascontiguousarray((coords / np.float32(2 ** i)).reshape(B, 1, H, W, 2))
+        gi = np.ascontiguousarray(go[:, i][:, None])
+        g1, g2, gc0 = orc.altcorr_backward(f1, f2, ci, gi, r)
+        assert not gc0.any()  # reference quirk: coords_grad never written
+        _, _, gc = orc.altcorr_backward(f1, f2, ci, gi, r, true_coords_grad=True)
+        df1 += g1
+        dco += gc[:, 0] / np.float32(2 ** i)
+        g2 = g2.transpose(0, 3, 1, 2)  # back to NCHW at level i
+        for _ in range(i):  # avg-pool backward: each fine cell of a pooled block gets grad/4
+            up = np.zeros(g2.shape[:2] + (g2.shape[2] * 2, g2.shape[3] * 2), np.float32)
+            for dy in (0, 1):
+                for dx in (0, 1):
+                    up[:, :, dy::2, dx::2] = g2 / 4
+            g2 = up
+        df2[:, :, :g2.shape[2], :g2.shape[3]] += g2
+    assert rel_err(df1.transpose(0, 3, 1, 2), g["df1"]) < GRAD_TOL
+    assert rel_err(df2, g["df2"]) < GRAD_TOL
+    assert rel_err(dco.transpose(0, 3, 1, 2), g["dcoords"]) < GRAD_TOL
+
+
+def test_real_features_raft_small_crop():
+    """Features/coords recorded from the reference RAFT-small run on demo frames (12 iterations)."""
+    g = load_golden("raft_small_crop")
+    B, C, H, W, L, r, _ = [int(v) for v in g["meta"]]
+    blk = orc.OracleCorrBlock(g["fmap1"], g["fmap2"], num_levels=L, radius=r)
+    for k in range(len(g["iters"])):
+        out = blk(g["coords"][k])[:, :, ::2, ::2]
+        assert rel_err(out, g["out_sub"][k]) < FWD_TOL
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/core"), reason="reference checkout not present")
+def test_oracle_vs_live_reference_midsize():
+    """Build container only: a larger seeded case straight against the imported reference."""
+    import sys
+    import warnings
+    import torch
+    warnings.filterwarnings("ignore")
+    sys.path.insert(0, "/root/reference/core")
+    try:
+        from corr import CorrBlock
+    finally:
+        sys.path.remove("/root/reference/core")
+        for m in ("corr", "utils", "utils.utils"):
+            sys.modules.pop(m, None)
+    rs = np.random.RandomState(7)
+    B, C, H, W, L, r = 1, 64, 23, 39, 4, 4   # 23x39 -> 11x19 -> 5x9 -> 2x4 (odd at every level)
+    f1 = (0.75 * rs.standard_normal((B, C, H, W))).astype(np.float32)
+    f2 = (0.75 * rs.standard_normal((B, C, H, W))).astype(np.float32)
+    ys, xs = np.meshgrid(np.arange(H), np.arange(W), indexing="ij")
+    coords = (np.stack([xs, ys])[None] + 4.0 * rs.standard_normal((B, 2, H, W))).astype(np.float32)
+    with torch.no_grad():
+        ref = CorrBlock(torch.from_numpy(f1), torch.from_numpy(f2), num_levels=L, radius=r)
+        want = ref(torch.from_numpy(coords)).numpy()
+    blk = orc.OracleCorrBlock(f1, f2, num_levels=L, radius=r)
+    for i in range(L):
+        assert rel_err(blk.corr_pyramid[i], ref.corr_pyramid[i].numpy()[:, 0]) < FWD_TOL
+    assert rel_err(blk(coords), want) < FWD_TOL
+    assert rel_err(orc.OracleAlternateCorrBlock(f1, f2, L, r)(coords), want) < 2e-5
