@@ -1,0 +1,9 @@
+"""B200-native (sm_100a) implementation of RAFT's correlation hot path.
+
+Public surface (mirrors the reference's core/corr.py and alt_cuda_corr extension):
+    from raft_optical_flow_b200 import CorrBlock, AlternateCorrBlock, alt_cuda_corr
+"""
+from . import alt_cuda_corr  # noqa: F401
+from .corr import AlternateCorrBlock, CorrBlock  # noqa: F401
+
+__all__ = ["CorrBlock", "AlternateCorrBlock", "alt_cuda_corr"]

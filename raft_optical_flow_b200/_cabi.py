@@ -1,0 +1,88 @@
+"""ctypes binding of libraftcorr_b200.so (include/raft_corr_b200.h).
+
+The library is the product: if it is missing or fails to load, importing the operators raises --
+there is no CPU or PyTorch fallback.
+"""
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libraftcorr_b200.so")
+
+MAX_LEVELS = 4
+MAX_RADIUS = 4
+
+# enum rcb_dtype / rcb_build_mode
+F32, F16 = 0, 1
+BUILD_FP32_SIMT, BUILD_BF16X3, BUILD_BF16 = 0, 1, 2
+BUILD_MODES = {"fp32": BUILD_FP32_SIMT, "bf16x3": BUILD_BF16X3, "bf16": BUILD_BF16}
+
+_vp = ctypes.c_void_p
+_i = ctypes.c_int
+
+
+class PyramidLayout(ctypes.Structure):
+    _fields_ = [
+        ("levels", ctypes.c_int32),
+        ("dtype", ctypes.c_int32),
+        ("H", ctypes.c_int32 * MAX_LEVELS),
+        ("W", ctypes.c_int32 * MAX_LEVELS),
+        ("row_stride", ctypes.c_int32 * MAX_LEVELS),
+        ("plane_stride", ctypes.c_int64 * MAX_LEVELS),
+        ("level_bytes", ctypes.c_int64 * MAX_LEVELS),
+    ]
+
+
+# name -> (restype, argtypes); every symbol include/raft_corr_b200.h declares
+SIGNATURES = {
+    "rcb_abi_version": (_i, []),
+    "rcb_status_string": (ctypes.c_char_p, [_i]),
+    "rcb_pyramid_layout_query": (_i, [_i, _i, _i, _i, _i, ctypes.POINTER(PyramidLayout)]),
+    "rcb_corr_build_workspace_bytes": (ctypes.c_size_t, [_i, _i, _i, _i, _i]),
+    "rcb_corr_build": (_i, [_vp, _vp, ctypes.POINTER(_vp), _i, _i, _i, _i, _i, _i, _i, _vp, ctypes.c_size_t, _vp]),
+    "rcb_corr_lookup": (_i, [ctypes.POINTER(_vp), _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "rcb_corr_lookup_backward": (_i, [ctypes.POINTER(_vp), _vp, _vp, ctypes.POINTER(_vp), _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "rcb_corr_pool_backward": (_i, [ctypes.POINTER(_vp), _i, _i, _i, _i, _vp]),
+    "rcb_corr_contract_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "rcb_altcorr_forward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "rcb_altcorr_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "rcb_altcorr_prepare": (_i, [_vp, _vp, _vp, ctypes.POINTER(_vp), _i, _i, _i, _i, _i, _vp]),
+    "rcb_altcorr_pyramid_forward": (_i, [_vp, ctypes.POINTER(_vp), _vp, _vp, _i, _i, _i, _i, _i, _i, ctypes.c_float, _vp]),
+}
+
+_lib = None
+
+
+def lib():
+    """Loads the shared library (once).  Raises if it has not been built: no fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -m raft_optical_flow_b200.build` "
+                "(nvcc, sm_100a).  raft_optical_flow_b200 has no CPU/PyTorch fallback.")
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)  # AttributeError if the library does not export the ABI
+            fn.restype = res
+            fn.argtypes = args
+        if handle.rcb_abi_version() != 1:
+            raise RuntimeError("libraftcorr_b200.so ABI version mismatch")
+        _lib = handle
+    return _lib
+
+
+def check(status, what):
+    if status != 0:
+        msg = lib().rcb_status_string(status).decode()
+        raise RuntimeError(f"{what} failed: {msg} (status {status})")
+
+
+def ptr_array(ptrs):
+    return (_vp * len(ptrs))(*[_vp(p) for p in ptrs])
+
+
+def pyramid_layout(B, H, W, levels, dtype=F32):
+    lay = PyramidLayout()
+    check(lib().rcb_pyramid_layout_query(B, H, W, levels, dtype, ctypes.byref(lay)), "rcb_pyramid_layout_query")
+    return lay

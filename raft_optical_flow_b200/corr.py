@@ -1,0 +1,245 @@
+"""Drop-in replacement for the reference's ``core/corr.py``.
+
+Same classes, constructor/call signatures, attribute names and output layout as the reference
+(``CorrBlock`` core/corr.py:12-127, ``AlternateCorrBlock`` core/corr.py:130-198); the arithmetic runs in
+hand-written sm_100a kernels behind the C ABI of ``include/raft_corr_b200.h``.  PyTorch is used for
+device memory, streams and autograd plumbing only.  There is no CPU path: tensors must live on a CUDA
+device (same error text as the reference extension, alt_cuda_corr/correlation.cpp:19).
+
+Build modes of the all-pairs volume (``mode=`` / env ``RAFT_CORR_MODE``):
+  "bf16x3" (default)  tcgen05 tensor cores, hi/lo bf16 split, fp32 accumulate  -> fp32-parity (<=1e-4 rel)
+  "fp32"              fp32 FMA pipe, the reference's exact arithmetic class
+  "bf16"              single-pass bf16 operands (fast mode, ~1e-3 rel)
+"""
+import math
+import os
+
+import torch
+import torch.nn.functional as F
+
+from . import _cabi
+
+__all__ = ["CorrBlock", "AlternateCorrBlock"]
+
+DEFAULT_MODE = os.environ.get("RAFT_CORR_MODE", "bf16x3")
+
+
+def _stream(t):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _check_cuda(t, name):
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor")
+
+
+def _prep(t, name):
+    _check_cuda(t, name)
+    return t.detach().float().contiguous()
+
+
+class _Pyramid:
+    """Device buffers of one correlation pyramid in the layout rcb_pyramid_layout_query reports."""
+
+    def __init__(self, B, H, W, levels, device, dtype=_cabi.F32, zero=False):
+        self.B, self.H, self.W, self.levels, self.dtype = B, H, W, levels, dtype
+        self.layout = _cabi.pyramid_layout(B, H, W, levels, dtype)
+        tdtype = torch.float32 if dtype == _cabi.F32 else torch.float16
+        esize = 4 if dtype == _cabi.F32 else 2
+        alloc = torch.zeros if zero else torch.empty
+        self.bufs = [alloc(self.layout.level_bytes[l] // esize, dtype=tdtype, device=device) for l in range(levels)]
+        self.ptrs = _cabi.ptr_array([b.data_ptr() for b in self.bufs])
+
+    def views(self):
+        """[B*H*W, 1, H_l, W_l] views, the shape of the reference's corr_pyramid entries (core/corr.py:44-54)."""
+        lay, n = self.layout, self.B * self.H * self.W
+        return [self.bufs[l].as_strided((n, 1, lay.H[l], lay.W[l]), (lay.plane_stride[l], 0, lay.row_stride[l], 1))
+                for l in range(self.levels)]
+
+    def zero_(self):
+        for b in self.bufs:
+            b.zero_()
+
+
+def _build(f1, f2, levels, mode, pyr):
+    B, C, H, W = f1.shape
+    lib = _cabi.lib()
+    ws_bytes = lib.rcb_corr_build_workspace_bytes(B, C, H, W, mode)
+    ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=f1.device)
+    with torch.cuda.device(f1.device):
+        _cabi.check(lib.rcb_corr_build(f1.data_ptr(), f2.data_ptr(), pyr.ptrs, B, C, H, W, levels, mode, pyr.dtype,
+                                       ws.data_ptr(), ws_bytes, _stream(f1)), "rcb_corr_build")
+    ws.record_stream(torch.cuda.current_stream(f1.device))
+
+
+class _BuildFn(torch.autograd.Function):
+    """Volume + pyramid.  The pyramid lives in ``state``; autograd sees a scalar token so that this node's
+    backward runs once, after every lookup of the forward pass has scattered its gradient."""
+
+    @staticmethod
+    def forward(ctx, fmap1, fmap2, state):
+        ctx.state = state
+        return torch.zeros((), device=fmap1.device)
+
+    @staticmethod
+    def backward(ctx, _grad_token):
+        st = ctx.state
+        B, C, H, W = st.f1.shape
+        lib = _cabi.lib()
+        df1 = torch.empty_like(st.f1)
+        df2 = torch.empty_like(st.f2)
+        if st.dpyr is None:  # no lookup contributed a gradient
+            return df1.zero_(), df2.zero_(), None
+        with torch.cuda.device(st.f1.device):
+            s = _stream(st.f1)
+            _cabi.check(lib.rcb_corr_pool_backward(st.dpyr.ptrs, B, H, W, st.levels, s), "rcb_corr_pool_backward")
+            _cabi.check(lib.rcb_corr_contract_backward(st.f1.data_ptr(), st.f2.data_ptr(), st.dpyr.bufs[0].data_ptr(),
+                                                       df1.data_ptr(), df2.data_ptr(), B, C, H, W, s),
+                        "rcb_corr_contract_backward")
+        st.dpyr = None  # a second backward pass starts from zero again
+        return df1, df2, None
+
+
+class _LookupFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, coords, token, state):
+        ctx.state = state
+        c = _prep(coords, "coords")
+        ctx.save_for_backward(c)
+        ctx.needs_pyr = token is not None and token.requires_grad
+        return state.lookup(c)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        st = ctx.state
+        (c,) = ctx.saved_tensors
+        B, _, H, W = c.shape
+        go = grad_out.float().contiguous()
+        want_c = ctx.needs_input_grad[0]
+        dco = torch.empty_like(c) if want_c else None
+        if ctx.needs_pyr and st.dpyr is None:
+            st.dpyr = _Pyramid(B, H, W, st.levels, c.device, _cabi.F32, zero=True)
+        if ctx.needs_pyr or want_c:
+            with torch.cuda.device(c.device):
+                _cabi.check(_cabi.lib().rcb_corr_lookup_backward(
+                    st.pyr.ptrs, c.data_ptr(), go.data_ptr(), st.dpyr.ptrs if ctx.needs_pyr else None,
+                    dco.data_ptr() if want_c else None, B, H, W, st.levels, st.radius, st.pyr.dtype, _stream(c)),
+                    "rcb_corr_lookup_backward")
+        dtoken = torch.zeros((), device=c.device) if ctx.needs_pyr else None
+        return dco, dtoken, None
+
+
+class _State:
+    """Everything one CorrBlock owns on the device."""
+
+    def __init__(self, f1, f2, levels, radius, mode, pyr_dtype):
+        B, C, H, W = f1.shape
+        self.f1, self.f2, self.levels, self.radius = f1, f2, levels, radius
+        self.pyr = _Pyramid(B, H, W, levels, f1.device, pyr_dtype)
+        self.dpyr = None
+        _build(f1, f2, levels, mode, self.pyr)
+
+    def lookup(self, coords):
+        B, two, H, W = coords.shape
+        if (B, H, W) != (self.pyr.B, self.pyr.H, self.pyr.W) or two != 2:
+            raise RuntimeError(f"coords shape {tuple(coords.shape)} does not match the feature maps")
+        rd = 2 * self.radius + 1
+        out = torch.empty((B, self.levels * rd * rd, H, W), dtype=torch.float32, device=coords.device)
+        with torch.cuda.device(coords.device):
+            _cabi.check(_cabi.lib().rcb_corr_lookup(self.pyr.ptrs, coords.data_ptr(), out.data_ptr(), B, H, W,
+                                                    self.levels, self.radius, self.pyr.dtype, _stream(coords)),
+                        "rcb_corr_lookup")
+        return out
+
+
+class CorrBlock:
+    """All-pairs correlation pyramid with per-iteration window lookup (reference core/corr.py:12-94)."""
+
+    def __init__(self, fmap1, fmap2, num_levels=4, radius=4, mode=None, pyramid_dtype="f32"):
+        self.num_levels = num_levels
+        self.radius = radius
+        if fmap1.shape != fmap2.shape or fmap1.dim() != 4:
+            raise RuntimeError("fmap1 and fmap2 must be [N, C, H, W] tensors of equal shape")
+        if not 1 <= num_levels <= _cabi.MAX_LEVELS or not 1 <= radius <= _cabi.MAX_RADIUS:
+            raise RuntimeError(f"num_levels must be in 1..{_cabi.MAX_LEVELS} and radius in 1..{_cabi.MAX_RADIUS}")
+        mode = _cabi.BUILD_MODES[mode or DEFAULT_MODE]
+        pyr_dtype = {"f32": _cabi.F32, "f16": _cabi.F16}[pyramid_dtype]
+        f1, f2 = _prep(fmap1, "fmap1"), _prep(fmap2, "fmap2")
+        self._state = _State(f1, f2, num_levels, radius, mode, pyr_dtype)
+        self._token = None
+        if torch.is_grad_enabled() and (fmap1.requires_grad or fmap2.requires_grad):
+            self._token = _BuildFn.apply(fmap1, fmap2, self._state)
+        self.corr_pyramid = self._state.pyr.views()
+
+    def __call__(self, coords):
+        if torch.is_grad_enabled() and (self._token is not None or coords.requires_grad):
+            return _LookupFn.apply(coords, self._token, self._state)
+        return self._state.lookup(_prep(coords, "coords"))
+
+    @staticmethod
+    def corr(fmap1, fmap2, mode=None):
+        """[N,C,H,W] x2 -> [N,H,W,1,H,W] = fmap1^T fmap2 / sqrt(C) (reference core/corr.py:96-127)."""
+        f1, f2 = _prep(fmap1, "fmap1"), _prep(fmap2, "fmap2")
+        B, C, H, W = f1.shape
+        pyr = _Pyramid(B, H, W, 1, f1.device)
+        _build(f1, f2, 1, _cabi.BUILD_MODES[mode or DEFAULT_MODE], pyr)
+        lay = pyr.layout
+        return pyr.bufs[0].as_strided((B, H, W, 1, H, W),
+                                      (H * W * lay.plane_stride[0], W * lay.plane_stride[0], lay.plane_stride[0], 0,
+                                       lay.row_stride[0], 1))
+
+
+class AlternateCorrBlock:
+    """On-the-fly correlation (reference core/corr.py:130-198): no Q x Q volume is ever stored; every call
+    evaluates the (2r+2)^2 tap dot products of each query at each level from pooled fmap2 features."""
+
+    def __init__(self, fmap1, fmap2, num_levels=4, radius=4):
+        self.num_levels = num_levels
+        self.radius = radius
+        if fmap1.shape != fmap2.shape or fmap1.dim() != 4:
+            raise RuntimeError("fmap1 and fmap2 must be [N, C, H, W] tensors of equal shape")
+        if not 1 <= num_levels <= _cabi.MAX_LEVELS or not 1 <= radius <= _cabi.MAX_RADIUS:
+            raise RuntimeError(f"num_levels must be in 1..{_cabi.MAX_LEVELS} and radius in 1..{_cabi.MAX_RADIUS}")
+        f1, f2 = _prep(fmap1, "fmap1"), _prep(fmap2, "fmap2")
+        B, C, H, W = f1.shape
+        self._shape = (B, C, H, W)
+        self._src = (f1, f2)
+        self._f1n = torch.empty((B, H, W, C), dtype=torch.float32, device=f1.device)
+        self._f2n = []
+        h, w = H, W
+        for _ in range(num_levels):
+            if h < 1 or w < 1:
+                raise RuntimeError("feature map too small for the requested number of levels")
+            self._f2n.append(torch.empty((B, h, w, C), dtype=torch.float32, device=f1.device))
+            h, w = h // 2, w // 2
+        self._f2ptrs = _cabi.ptr_array([t.data_ptr() for t in self._f2n])
+        with torch.cuda.device(f1.device):
+            _cabi.check(_cabi.lib().rcb_altcorr_prepare(f1.data_ptr(), f2.data_ptr(), self._f1n.data_ptr(),
+                                                        self._f2ptrs, B, C, H, W, num_levels, _stream(f1)),
+                        "rcb_altcorr_prepare")
+
+    @property
+    def pyramid(self):
+        """[(fmap1_i, fmap2_i)] with num_levels+1 entries like the reference (core/corr.py:154-161).  Only
+        pyramid[0][0] and pyramid[i][1] are ever used (core/corr.py:183-184); fmap2 entries are views of the
+        NHWC buffers the kernels read, the unused pooled fmap1 entries are materialised on demand."""
+        f1, f2 = self._src
+        out = [(f1, self._f2n[0].permute(0, 3, 1, 2))]
+        for i in range(1, self.num_levels + 1):
+            f1 = F.avg_pool2d(f1, 2, stride=2)
+            f2i = self._f2n[i].permute(0, 3, 1, 2) if i < self.num_levels else F.avg_pool2d(out[-1][1], 2, stride=2)
+            out.append((f1, f2i))
+        return out
+
+    def __call__(self, coords):
+        B, C, H, W = self._shape
+        c = _prep(coords, "coords")
+        if tuple(c.shape) != (B, 2, H, W):
+            raise RuntimeError(f"coords shape {tuple(c.shape)} does not match the feature maps")
+        rd = 2 * self.radius + 1
+        out = torch.empty((B, self.num_levels * rd * rd, H, W), dtype=torch.float32, device=c.device)
+        with torch.cuda.device(c.device):
+            _cabi.check(_cabi.lib().rcb_altcorr_pyramid_forward(
+                self._f1n.data_ptr(), self._f2ptrs, c.data_ptr(), out.data_ptr(), B, C, H, W, self.num_levels,
+                self.radius, 1.0 / math.sqrt(C), _stream(c)), "rcb_altcorr_pyramid_forward")
+        return out

@@ -1,0 +1,105 @@
+// Shared device/host helpers for libraftcorr_b200 (sm_100a only).
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/raft_corr_b200.h"
+
+#define RCB_DEVINL __device__ __forceinline__
+
+namespace rcb {
+
+constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
+
+inline int launch_status() {
+  cudaError_t e = cudaPeekAtLastError();
+  return e == cudaSuccess ? RCB_OK : (int)e;
+}
+
+// Pyramid geometry handed to kernels by value.
+struct PyramidDev {
+  const void* ptr[RCB_MAX_LEVELS];
+  int H[RCB_MAX_LEVELS];
+  int W[RCB_MAX_LEVELS];
+  int row_stride[RCB_MAX_LEVELS];
+  long long plane_stride[RCB_MAX_LEVELS];
+};
+
+inline int fill_layout(int B, int H, int W, int levels, int dtype, rcb_pyramid_layout* lay) {
+  if (!lay || B <= 0 || H <= 0 || W <= 0) return RCB_ERR_INVALID_ARGUMENT;
+  if (levels < 1 || levels > RCB_MAX_LEVELS) return RCB_ERR_UNSUPPORTED;
+  if (dtype != RCB_F32 && dtype != RCB_F16) return RCB_ERR_UNSUPPORTED;
+  const int esize = dtype == RCB_F32 ? 4 : 2;
+  const int align_elems = 16 / esize;
+  lay->levels = levels;
+  lay->dtype = dtype;
+  int h = H, w = W;
+  for (int l = 0; l < RCB_MAX_LEVELS; ++l) {
+    if (l < levels) {
+      if (h < 1 || w < 1) return RCB_ERR_INVALID_ARGUMENT;  // pooled away (reference would fail too)
+      lay->H[l] = h;
+      lay->W[l] = w;
+      lay->row_stride[l] = (w + align_elems - 1) / align_elems * align_elems;
+      lay->plane_stride[l] = (long long)h * lay->row_stride[l];
+      lay->level_bytes[l] = (long long)B * H * W * lay->plane_stride[l] * esize;
+      h /= 2;
+      w /= 2;
+    } else {
+      lay->H[l] = lay->W[l] = lay->row_stride[l] = 0;
+      lay->plane_stride[l] = lay->level_bytes[l] = 0;
+    }
+  }
+  return RCB_OK;
+}
+
+// ---- async copy (LDGSTS) with zero fill -------------------------------------------------
+RCB_DEVINL uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// 16-byte global->shared copy through L2 only; bytes beyond src_bytes are written as zero.
+RCB_DEVINL void cp_async16_zfill(uint32_t dst_smem, const void* src, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst_smem), "l"(src), "r"(src_bytes)
+               : "memory");
+}
+RCB_DEVINL void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+RCB_DEVINL void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+
+RCB_DEVINL float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+}  // namespace rcb
+
+// Launchers implemented in the individual .cu files (called from c_abi.cu).
+namespace rcb {
+int launch_build_simt(const float* f1, const float* f2, void* const* pyr, const rcb_pyramid_layout& lay, int B,
+                      int C, int H, int W, cudaStream_t s);
+int launch_pool_levels(void* const* pyr, const rcb_pyramid_layout& lay, int B, int H, int W, cudaStream_t s);
+size_t build_tc_workspace_bytes(int B, int C, int H, int W, int mode);
+int launch_build_tc(const float* f1, const float* f2, void* const* pyr, const rcb_pyramid_layout& lay, int B,
+                    int C, int H, int W, int mode, void* ws, size_t ws_bytes, cudaStream_t s);
+int launch_lookup(const void* const* pyr, const rcb_pyramid_layout& lay, const float* coords, float* out, int B,
+                  int H, int W, int radius, cudaStream_t s);
+int launch_lookup_backward(const void* const* pyr, const rcb_pyramid_layout& lay, const float* coords,
+                           const float* grad_out, float* const* dpyr, float* dcoords, int B, int H, int W,
+                           int radius, cudaStream_t s);
+int launch_pool_backward(float* const* dpyr, const rcb_pyramid_layout& lay, int B, int H, int W, cudaStream_t s);
+int launch_contract_backward(const float* f1, const float* f2, const float* dvol0, float* df1, float* df2, int B,
+                             int C, int H, int W, cudaStream_t s);
+int launch_altcorr_forward(const float* f1, const float* f2, const float* coords, float* corr, int B, int N, int H1,
+                           int W1, int H2, int W2, int C, int r, cudaStream_t s);
+int launch_altcorr_backward(const float* f1, const float* f2, const float* coords, const float* cg, float* g1,
+                            float* g2, float* gc, int B, int N, int H1, int W1, int H2, int W2, int C, int r,
+                            int true_cg, cudaStream_t s);
+int launch_altcorr_prepare(const float* f1, const float* f2, float* f1n, float* const* f2n, int B, int C, int H,
+                           int W, int levels, cudaStream_t s);
+int launch_altcorr_pyramid_forward(const float* f1n, const float* const* f2n, const float* coords, float* out,
+                                   int B, int C, int H, int W, int levels, int r, float scale, cudaStream_t s);
+}  // namespace rcb

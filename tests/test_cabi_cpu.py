@@ -1,0 +1,99 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/raft_corr_b200.h declares,
+host-only entry points behave, and the Python mirror keeps the reference's error behaviour.  No compute."""
+import ctypes
+import os
+import re
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from raft_optical_flow_b200 import _cabi, build as rcb_build  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def lib():
+    rcb_build.build()
+    return _cabi.lib()
+
+
+def header_symbols():
+    with open(os.path.join(ROOT, "include", "raft_corr_b200.h")) as f:
+        return sorted(set(re.findall(r"RCB_API\s+[\w\s\*]+?\b(rcb_\w+)\s*\(", f.read())))
+
+
+def test_library_exports_every_declared_symbol(lib):
+    syms = header_symbols()
+    assert len(syms) == 13
+    for s in syms:
+        assert hasattr(lib, s), s
+    assert sorted(_cabi.SIGNATURES) == syms  # the ctypes table binds exactly the header
+
+
+def test_status_strings(lib):
+    assert lib.rcb_abi_version() == 1
+    assert lib.rcb_status_string(0) == b"ok"
+    assert b"invalid" in lib.rcb_status_string(-1)
+    assert b"unsupported" in lib.rcb_status_string(-2)
+
+
+@pytest.mark.parametrize("H,W,want_h,want_w", [(55, 128, [55, 27, 13, 6], [128, 64, 32, 16]),
+                                               (47, 156, [47, 23, 11, 5], [156, 78, 39, 19]),
+                                               (46, 62, [46, 23, 11, 5], [62, 31, 15, 7])])
+def test_pyramid_layout_floor_halving_and_padding(lib, H, W, want_h, want_w):
+    lay = _cabi.pyramid_layout(3, H, W, 4)
+    assert list(lay.H) == want_h and list(lay.W) == want_w  # core/corr.py:52-54 floor mode
+    for l in range(4):
+        assert lay.row_stride[l] >= lay.W[l] and lay.row_stride[l] % 4 == 0  # 16-byte rows
+        assert lay.plane_stride[l] == lay.H[l] * lay.row_stride[l]
+        assert lay.level_bytes[l] == 3 * H * W * lay.plane_stride[l] * 4
+    half = _cabi.pyramid_layout(3, H, W, 4, _cabi.F16)
+    assert all(half.row_stride[l] % 8 == 0 for l in range(4))
+
+
+def test_layout_rejects_bad_arguments(lib):
+    lay = _cabi.PyramidLayout()
+    assert lib.rcb_pyramid_layout_query(1, 8, 8, 5, 0, ctypes.byref(lay)) == -2  # > RCB_MAX_LEVELS
+    assert lib.rcb_pyramid_layout_query(0, 8, 8, 4, 0, ctypes.byref(lay)) == -1
+    assert lib.rcb_pyramid_layout_query(1, 4, 4, 4, 0, ctypes.byref(lay)) == -1  # pooled away (4->2->1->0)
+
+
+def test_entry_points_validate_before_touching_the_device(lib):
+    null = _cabi.ptr_array([0, 0, 0, 0])
+    assert lib.rcb_corr_lookup(null, None, None, 1, 8, 8, 4, 4, 0, None) == -1
+    assert lib.rcb_corr_build(None, None, null, 1, 8, 8, 8, 4, 0, 0, None, 0, None) == -1
+    assert lib.rcb_altcorr_forward(None, None, None, None, 1, 1, 8, 8, 8, 8, 8, 4, None) == -1
+    buf = (ctypes.c_float * 64)()
+    p = ctypes.addressof(buf)
+    assert lib.rcb_altcorr_forward(p, p, p, p, 1, 1, 2, 2, 2, 2, 4, 9, None) == -2  # radius > RCB_MAX_RADIUS
+
+
+def test_python_mirror_has_no_cpu_path():
+    from raft_optical_flow_b200 import AlternateCorrBlock, CorrBlock, alt_cuda_corr
+    f = torch.zeros(1, 8, 8, 8)
+    with pytest.raises(RuntimeError, match="fmap1 must be a CUDA tensor"):  # correlation.cpp:19
+        CorrBlock(f, f)
+    with pytest.raises(RuntimeError, match="fmap1 must be a CUDA tensor"):
+        AlternateCorrBlock(f, f)
+    with pytest.raises(RuntimeError, match="fmap1 must be a CUDA tensor"):
+        alt_cuda_corr.forward(f.permute(0, 2, 3, 1).contiguous(), f, torch.zeros(1, 1, 8, 8, 2), 4)
+
+
+def test_dropin_modules_resolve_like_the_reference_imports():
+    """core/raft.py:8 does `from corr import CorrBlock, AlternateCorrBlock`; core/corr.py:6 `import alt_cuda_corr`."""
+    import importlib
+    sys.path.insert(0, os.path.join(ROOT, "dropin"))
+    try:
+        for m in ("corr", "alt_cuda_corr"):
+            sys.modules.pop(m, None)
+        corr = importlib.import_module("corr")
+        ext = importlib.import_module("alt_cuda_corr")
+        assert corr.CorrBlock.__init__.__code__.co_varnames[:5] == ("self", "fmap1", "fmap2", "num_levels", "radius")
+        assert callable(corr.CorrBlock.corr) and callable(ext.forward) and callable(ext.backward)
+    finally:
+        sys.path.remove(os.path.join(ROOT, "dropin"))
+        for m in ("corr", "alt_cuda_corr"):
+            sys.modules.pop(m, None)

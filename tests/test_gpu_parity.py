@@ -1,0 +1,317 @@
+"""Parity of the CUDA path (through the C ABI / Python mirror) against
+  (1) golden fixtures produced by the reference itself (tests/golden/),
+  (2) the CPU oracle on seeded inputs at sizes it finishes in seconds,
+  (3) size-independent properties at BASELINE.json's full sizes,
+  (4) the reference's own compiled alt_cuda_corr extension (oracle/_ref) when it travelled to the box.
+Tolerance (BASELINE.json north_star): fp32-parity modes max-abs error <= 1e-4 relative to the max-abs of
+the reference output; gradients 2e-4; the single-pass bf16 fast mode 5e-3.
+"""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import cotangent, load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4
+GRAD_TOL = 2e-4
+BF16_TOL = 5e-3
+PARITY_MODES = os.environ.get("RCB_TEST_MODES", "fp32,bf16x3").split(",")
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device (no CPU fallback exists)"
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def rcb():
+    import raft_optical_flow_b200 as pkg
+    from raft_optical_flow_b200 import _cabi
+    _cabi.lib()
+    return pkg
+
+
+@pytest.fixture(scope="module")
+def orc():
+    from oracle import oracle
+    return oracle
+
+
+def t(a, dev):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+def seeded(seed, B, C, H, W, sigma=4.0, mean=0.0, std=0.75):
+    rs = np.random.RandomState(seed)
+    f1 = (mean + std * rs.standard_normal((B, C, H, W))).astype(np.float32)
+    f2 = (mean + std * rs.standard_normal((B, C, H, W))).astype(np.float32)
+    ys, xs = np.meshgrid(np.arange(H), np.arange(W), indexing="ij")
+    coords = (np.stack([xs, ys])[None] + sigma * rs.standard_normal((B, 2, H, W))).astype(np.float32)
+    return f1, f2, coords
+
+
+# ---------------------------------------------------------------------------------------------
+# (1) golden fixtures from the reference
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mode", PARITY_MODES)
+@pytest.mark.parametrize("name", ["corrblock_odd", "corrblock_full_r4", "corrblock_small_r3", "corrblock_edges",
+                                  "corrblock_onehot"])
+def test_corrblock_golden(rcb, dev, name, mode):
+    g = load_golden(name)
+    B, C, H, W, L, r, _ = [int(v) for v in g["meta"]]
+    blk = rcb.CorrBlock(t(g["fmap1"], dev), t(g["fmap2"], dev), num_levels=L, radius=r, mode=mode)
+    assert blk.num_levels == L and blk.radius == r and len(blk.corr_pyramid) == L
+    for i in range(L):
+        lvl = blk.corr_pyramid[i]
+        assert lvl.shape[0] == B * H * W and lvl.shape[1] == 1
+        if f"pyr{i}" in g:
+            assert rel_err(lvl[:, 0].cpu().numpy(), g[f"pyr{i}"]) < TOL, f"level {i}"
+    out = blk(t(g["coords"], dev))
+    assert out.dtype == torch.float32 and out.is_contiguous() and tuple(out.shape) == g["out"].shape
+    assert rel_err(out.cpu().numpy(), g["out"]) < TOL
+
+
+def test_known_answers(rcb, dev):
+    g = load_golden("corrblock_onehot")
+    B, C, H, W, L, r, _ = [int(v) for v in g["meta"]]
+    rd = 2 * r + 1
+    out = rcb.CorrBlock(t(g["fmap1"], dev), t(g["fmap2"], dev), num_levels=L, radius=r, mode="fp32")(
+        t(g["coords"], dev)).cpu().numpy()
+    assert list(np.nonzero(out[0, :rd * rd, 5, 9])[0]) == [(1 + r) * rd + r]  # x offset is the slow index
+    assert list(np.nonzero(out[0, :rd * rd, 4, 10])[0]) == [r * rd + (1 + r)]
+    assert out[0, 17, 5, 9] == 1.0 and out[0, 13, 4, 10] == 1.0
+    far = rcb.CorrBlock(t(g["fmap1"], dev), t(g["fmap2"], dev), num_levels=L, radius=r, mode="fp32")(
+        t(g["coords"] + 1000.0, dev))
+    assert not far.any().item()
+
+
+def test_real_features_golden(rcb, dev):
+    g = load_golden("raft_small_crop")
+    B, C, H, W, L, r, _ = [int(v) for v in g["meta"]]
+    for mode in PARITY_MODES:
+        blk = rcb.CorrBlock(t(g["fmap1"], dev), t(g["fmap2"], dev), num_levels=L, radius=r, mode=mode)
+        alt = rcb.AlternateCorrBlock(t(g["fmap1"], dev), t(g["fmap2"], dev), num_levels=L, radius=r)
+        for k in range(len(g["iters"])):
+            c = t(g["coords"][k], dev)
+            assert rel_err(blk(c)[:, :, ::2, ::2].cpu().numpy(), g["out_sub"][k]) < TOL
+            assert rel_err(alt(c)[:, :, ::2, ::2].cpu().numpy(), g["out_sub"][k]) < TOL
+
+
+@pytest.mark.parametrize("name", ["corrblock_odd", "corrblock_full_r4"])
+def test_corrblock_backward_golden(rcb, dev, name):
+    """Gradients w.r.t. fmap1, fmap2 AND coords vs autograd through the reference CorrBlock."""
+    g = load_golden(name)
+    B, C, H, W, L, r, seed = [int(v) for v in g["meta"]]
+    f1 = t(g["fmap1"], dev).requires_grad_(True)
+    f2 = t(g["fmap2"], dev).requires_grad_(True)
+    co = t(g["coords"], dev).requires_grad_(True)
+    blk = rcb.CorrBlock(f1, f2, num_levels=L, radius=r, mode="fp32")
+    out = blk(co)
+    out.backward(t(cotangent(seed, g["out"].shape), dev))
+    assert rel_err(f1.grad.cpu().numpy(), g["df1"]) < GRAD_TOL
+    assert rel_err(f2.grad.cpu().numpy(), g["df2"]) < GRAD_TOL
+    assert rel_err(co.grad.cpu().numpy(), g["dcoords"]) < GRAD_TOL
+
+
+def test_backward_accumulates_over_iterations(rcb, dev, orc):
+    """train.py runs 12 lookups per forward; their gradients must add up in one backward pass."""
+    f1n, f2n, c0 = seeded(5, 1, 16, 12, 16, sigma=2.0)
+    _, _, c1 = seeded(6, 1, 16, 12, 16, sigma=2.0)
+    L, r = 3, 3
+    f1 = t(f1n, dev).requires_grad_(True)
+    f2 = t(f2n, dev).requires_grad_(True)
+    blk = rcb.CorrBlock(f1, f2, num_levels=L, radius=r, mode="fp32")
+    o0, o1 = blk(t(c0, dev)), blk(t(c1, dev))
+    g0, g1 = cotangent(11, tuple(o0.shape)), cotangent(12, tuple(o1.shape))
+    (o0 * t(g0, dev)).sum().add((o1 * t(g1, dev)).sum()).backward()
+    ob = orc.OracleCorrBlock(f1n, f2n, L, r)
+    a1, a2, _ = ob.backward(c0, g0)
+    b1, b2, _ = ob.backward(c1, g1)
+    assert rel_err(f1.grad.cpu().numpy(), a1 + b1) < GRAD_TOL
+    assert rel_err(f2.grad.cpu().numpy(), a2 + b2) < GRAD_TOL
+
+
+# ---------------------------------------------------------------------------------------------
+# (2) CPU oracle on seeded inputs
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mode", PARITY_MODES)
+@pytest.mark.parametrize("shape", [(2, 64, 23, 39, 4, 4), (1, 128, 55, 128, 4, 3), (1, 256, 46, 62, 4, 4),
+                                   (3, 32, 9, 17, 2, 1), (1, 48, 16, 33, 3, 2)])
+def test_corrblock_vs_oracle(rcb, dev, orc, shape, mode):
+    B, C, H, W, L, r = shape
+    f1, f2, coords = seeded(100 + H, B, C, H, W)
+    want_blk = orc.OracleCorrBlock(f1, f2, L, r)
+    blk = rcb.CorrBlock(t(f1, dev), t(f2, dev), num_levels=L, radius=r, mode=mode)
+    for i in range(L):
+        assert rel_err(blk.corr_pyramid[i][:, 0].cpu().numpy(), want_blk.corr_pyramid[i]) < TOL, f"level {i}"
+    assert rel_err(blk(t(coords, dev)).cpu().numpy(), want_blk(coords)) < TOL
+
+
+def test_mean_heavy_features(rcb, dev, orc):
+    """Random-init RAFT-full features are mean-heavy (SURVEY 7 'Precision'): corr mean ~17, |max| ~39."""
+    f1, f2, coords = seeded(77, 1, 256, 24, 40, mean=1.0, std=1.45)
+    want = orc.OracleCorrBlock(f1, f2, 4, 4)(coords)
+    for mode in PARITY_MODES:
+        got = rcb.CorrBlock(t(f1, dev), t(f2, dev), mode=mode)(t(coords, dev)).cpu().numpy()
+        assert rel_err(got, want) < TOL, mode
+    if "bf16x3" in PARITY_MODES:
+        fast = rcb.CorrBlock(t(f1, dev), t(f2, dev), mode="bf16")(t(coords, dev)).cpu().numpy()
+        assert rel_err(fast, want) < BF16_TOL
+
+
+def test_corr_static_method(rcb, dev, orc):
+    f1, f2, _ = seeded(3, 2, 32, 10, 14)
+    v = rcb.CorrBlock.corr(t(f1, dev), t(f2, dev), mode="fp32")
+    assert tuple(v.shape) == (2, 10, 14, 1, 10, 14)
+    assert rel_err(v.reshape(2, 140, 140).cpu().numpy(), orc.corr_volume(f1, f2)) < TOL
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 23, 39, 4, 4), (1, 128, 30, 44, 4, 3), (1, 256, 16, 24, 3, 4)])
+def test_alternate_block_vs_oracle(rcb, dev, orc, shape):
+    B, C, H, W, L, r = shape
+    f1, f2, coords = seeded(200 + H, B, C, H, W)
+    want = orc.OracleAlternateCorrBlock(f1, f2, L, r)(coords)
+    alt = rcb.AlternateCorrBlock(t(f1, dev), t(f2, dev), num_levels=L, radius=r)
+    assert rel_err(alt(t(coords, dev)).cpu().numpy(), want) < TOL
+    pyr = alt.pyramid
+    assert len(pyr) == L + 1 and tuple(pyr[1][1].shape) == (B, C, H // 2, W // 2)
+
+
+def _ext_inputs(seed, B, N, H1, W1, H2, W2, C, sigma=3.0):
+    rs = np.random.RandomState(seed)
+    f1 = rs.standard_normal((B, H1, W1, C)).astype(np.float32)
+    f2 = rs.standard_normal((B, H2, W2, C)).astype(np.float32)
+    ys, xs = np.meshgrid(np.arange(H1), np.arange(W1), indexing="ij")
+    base = np.stack([xs, ys], -1)[None, None].astype(np.float32) * (W2 / W1)
+    coords = (base + sigma * rs.standard_normal((B, N, H1, W1, 2))).astype(np.float32)
+    return f1, f2, coords
+
+
+@pytest.mark.parametrize("dims", [(2, 1, 12, 20, 12, 20, 64, 4), (1, 2, 16, 24, 8, 12, 128, 3),
+                                  (1, 1, 9, 13, 4, 6, 32, 2)])
+def test_alt_cuda_corr_extension_vs_oracle(rcb, dev, orc, dims):
+    B, N, H1, W1, H2, W2, C, r = dims
+    f1, f2, coords = _ext_inputs(31, B, N, H1, W1, H2, W2, C)
+    (corr,) = rcb.alt_cuda_corr.forward(t(f1, dev), t(f2, dev), t(coords, dev), r)
+    want = orc.altcorr_forward(f1, f2, coords, r)
+    assert tuple(corr.shape) == want.shape
+    assert rel_err(corr.cpu().numpy(), want) < TOL
+    cg = cotangent(32, want.shape)
+    g1, g2, gc = rcb.alt_cuda_corr.backward(t(f1, dev), t(f2, dev), t(coords, dev), t(cg, dev), r)
+    w1, w2, _ = orc.altcorr_backward(f1, f2, coords, cg, r)
+    assert rel_err(g1.cpu().numpy(), w1) < GRAD_TOL
+    assert rel_err(g2.cpu().numpy(), w2) < GRAD_TOL
+    assert not gc.any().item()  # reference quirk: coords_grad is never written (correlation_kernel.cu:307)
+    _, _, gct = rcb.alt_cuda_corr.backward(t(f1, dev), t(f2, dev), t(coords, dev), t(cg, dev), r,
+                                           true_coords_grad=True)
+    _, _, wct = orc.altcorr_backward(f1, f2, coords, cg, r, true_coords_grad=True)
+    assert rel_err(gct.cpu().numpy(), wct) < GRAD_TOL
+
+
+# ---------------------------------------------------------------------------------------------
+# (4) the reference's own compiled extension, on the same GPU
+# ---------------------------------------------------------------------------------------------
+def _load_ref_ext():
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "alt_cuda_corr.so")
+    if not os.path.exists(path):
+        return None
+    spec = importlib.util.spec_from_file_location("alt_cuda_corr", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_alt_cuda_corr_vs_reference_extension(rcb, dev):
+    ref = _load_ref_ext()
+    if ref is None:
+        pytest.skip("oracle/_ref/alt_cuda_corr.so not built (reference checkout absent at build time)")
+    # H1, W1 multiples of the reference's 4x8 block: its backward reads coords out of bounds otherwise
+    B, N, H1, W1, H2, W2, C, r = 2, 1, 16, 24, 8, 12, 256, 4
+    f1, f2, coords = _ext_inputs(41, B, N, H1, W1, H2, W2, C)
+    a = [t(x, dev) for x in (f1, f2, coords)]
+    torch.cuda.synchronize()
+    (want,) = ref.forward(*a, r)  # launches on the legacy default stream
+    torch.cuda.synchronize()
+    (got,) = rcb.alt_cuda_corr.forward(*a, r)
+    assert rel_err(got.cpu().numpy(), want.cpu().numpy()) < TOL
+    cg = t(cotangent(42, tuple(want.shape)), dev)
+    w1, w2, wc = ref.backward(*a, cg, r)
+    torch.cuda.synchronize()
+    g1, g2, gc = rcb.alt_cuda_corr.backward(*a, cg, r)
+    assert rel_err(g1.cpu().numpy(), w1.cpu().numpy()) < GRAD_TOL
+    assert rel_err(g2.cpu().numpy(), w2.cpu().numpy()) < GRAD_TOL
+    assert not wc.any().item() and not gc.any().item()
+
+
+# ---------------------------------------------------------------------------------------------
+# (3) size-independent properties at full size (BASELINE.json configs)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mode", PARITY_MODES)
+@pytest.mark.parametrize("cfg", [(2, 256, 55, 128, 4), (2, 256, 47, 156, 4), (1, 128, 55, 128, 3)])
+def test_full_size_properties(rcb, dev, cfg, mode):
+    B, C, H, W, r = cfg
+    L, rd = 4, 2 * r + 1
+    gen = torch.Generator(device="cpu").manual_seed(1234)
+    f1 = (0.75 * torch.randn(B, C, H, W, generator=gen)).to(dev)
+    f2 = (0.75 * torch.randn(B, C, H, W, generator=gen)).to(dev)
+    blk = rcb.CorrBlock(f1, f2, num_levels=L, radius=r, mode=mode)
+    pyr = blk.corr_pyramid
+    # level 0 against a plain fp32 (non-TF32) torch contraction in float64 on a slab of queries
+    q = torch.arange(0, H * W, 97, device=dev)
+    a = f1.reshape(B, C, H * W)[0][:, q].double().T @ f2.reshape(B, C, H * W)[0].double() / np.sqrt(C)
+    got0 = pyr[0][:H * W, 0].reshape(H * W, H * W)[q].double()
+    assert ((got0 - a).abs().max() / a.abs().max()).item() < TOL
+    # level l is the floor-mode 2x2 mean of level l-1 (core/corr.py:52-54)
+    for l in range(1, L):
+        want = torch.nn.functional.avg_pool2d(pyr[l - 1].contiguous(), 2, stride=2)
+        assert tuple(want.shape) == tuple(pyr[l].shape)
+        assert ((pyr[l] - want).abs().max() / want.abs().max()).item() < 1e-6
+    # integer coords: centre channel of level 0 is <F1[q], F2[q]> / sqrt(C)
+    ys, xs = torch.meshgrid(torch.arange(H, device=dev), torch.arange(W, device=dev), indexing="ij")
+    grid = torch.stack([xs, ys]).float()[None].repeat(B, 1, 1, 1)
+    out = blk(grid)
+    centre = out[:, r * rd + r]
+    want = (f1.double() * f2.double()).sum(1) / np.sqrt(C)
+    assert ((centre.double() - want).abs().max() / want.abs().max()).item() < TOL
+    # far outside -> exact zeros; lookup is linear in the pyramid -> all-pairs == on-the-fly formulation
+    assert not blk(grid + 4096.0).any().item()
+    coords = grid + 4.0 * torch.randn(B, 2, H, W, generator=gen).to(dev)
+    alt = rcb.AlternateCorrBlock(f1, f2, num_levels=L, radius=r)
+    o1, o2 = blk(coords), alt(coords)
+    assert ((o1 - o2).abs().max() / o2.abs().max()).item() < TOL
+    # transposition symmetry of the volume: corr(f1,f2)[q,p] == corr(f2,f1)[p,q]
+    v12 = pyr[0][:H * W, 0].reshape(H * W, H * W)
+    v21 = rcb.CorrBlock(f2, f1, num_levels=1, radius=r, mode=mode).corr_pyramid[0][:H * W, 0].reshape(H * W, H * W)
+    assert ((v12 - v21.T).abs().max() / v12.abs().max()).item() < TOL
+
+
+# ---------------------------------------------------------------------------------------------
+# boundary behaviour
+# ---------------------------------------------------------------------------------------------
+def test_error_behaviour_matches_reference_extension(rcb, dev):
+    f = torch.zeros(1, 8, 8, 16, device=dev)
+    c = torch.zeros(1, 1, 8, 8, 2, device=dev)
+    with pytest.raises(RuntimeError, match="fmap2 must be a CUDA tensor"):
+        rcb.alt_cuda_corr.forward(f, f.cpu(), c, 4)
+    with pytest.raises(RuntimeError, match="fmap1 must be contiguous"):
+        rcb.alt_cuda_corr.forward(f.permute(0, 2, 1, 3), f, c, 4)
+    with pytest.raises(RuntimeError):
+        rcb.CorrBlock(torch.zeros(1, 8, 8, 8, device=dev), torch.zeros(1, 8, 8, 8, device=dev), radius=9)
+
+
+def test_runs_on_the_callers_stream(rcb, dev, orc):
+    f1, f2, coords = seeded(9, 1, 32, 16, 24)
+    want = orc.OracleCorrBlock(f1, f2, 4, 4)(coords)
+    s = torch.cuda.Stream(device=dev)
+    a, b, c = t(f1, dev), t(f2, dev), t(coords, dev)
+    torch.cuda.synchronize()
+    with torch.cuda.stream(s):
+        out = rcb.CorrBlock(a, b, mode="fp32")(c)
+    s.synchronize()
+    assert rel_err(out.cpu().numpy(), want) < TOL
