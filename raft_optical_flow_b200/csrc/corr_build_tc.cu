@@ -1,9 +1,605 @@
-// K1 tensor-core modes (placeholder until the tcgen05 kernel lands in this file).
+// K1, tensor-core modes: all-pairs correlation volume + fused 4-level pooled pyramid in ONE kernel.
+//
+// Replaces CorrBlock.corr (reference core/corr.py:96-127: matmul + / sqrt(C)) and the avg_pool2d loop of
+// CorrBlock.__init__ (core/corr.py:52-54).  See DESIGN.md "K1" for the roofline discussion: with an fp32
+// pyramid the kernel is bound by the 2.2 GB of stores, so the design goal is to keep the tensor pipe and the
+// operand traffic below the store time and to overlap everything with the epilogue.
+//
+//   pack kernel   fp32 NCHW feature maps -> bf16 K-major [part][B][Q][Kp] (part 0 = hi, part 1 = lo = x - hi),
+//                 i.e. a transpose + split.  RCB_BUILD_BF16X3 evaluates  hi*hi + hi*lo + lo*hi  (error ~2e-6 of
+//                 max-abs); RCB_BUILD_BF16 uses the hi parts only.
+//   main kernel   persistent, warp-specialised, one CTA per SM, 192 threads:
+//     warp 0      TMA producer.  A (128 queries x Kp, hi and lo) is loaded once per work unit and stays
+//                 resident in shared memory; B tiles (an 8 x 16 PATCH of target pixels x 64 channels, fetched
+//                 as one 4-D TMA box of the [part*B, H, W, Kp] tensor, out-of-image rows/cols zero-filled)
+//                 stream through a 4-stage mbarrier ring.
+//     warp 1      MMA issuer: tcgen05.mma.cta_group::1.kind::f16, M=128, N=128, K=16, SWIZZLE_128B K-major
+//                 smem descriptors, fp32 accumulators in TMEM, 4 accumulator buffers (512 columns).
+//     warps 2-5   epilogue: tcgen05.ld (lane = query, 32 columns = 2 patch rows x 16 targets), scale by
+//                 1/sqrt(C); level 0 goes through a swizzled staging buffer and a 4-D TMA store (the
+//                 store clips rows/cols/queries outside the tensor); levels 1-3 are 2x2 means formed in
+//                 registers from the same accumulator values -- the patch is 8x8-aligned, so all three
+//                 pooled levels are tile-local; floor-mode dropping of odd rows/cols falls out of the
+//                 store clipping (level k cell j is valid iff j < floor(H_{k-1}/2)).  Level 1 is TMA-stored,
+//                 levels 2/3 (6% / 1.5% of the bytes) are written with 16/8-byte global stores.
+#include <cudaTypedefs.h>
+
+#include <cstdlib>
+
 #include "rcb_common.cuh"
+
 namespace rcb {
-size_t build_tc_workspace_bytes(int, int, int, int, int) { return 0; }
-int launch_build_tc(const float*, const float*, void* const*, const rcb_pyramid_layout&, int, int, int, int, int,
-                    void*, size_t, cudaStream_t) {
-  return RCB_ERR_UNSUPPORTED;
+
+namespace tc {
+
+constexpr int BM = 128;          // queries per tile (TMEM lanes)
+constexpr int PH = 8, PW = 16;   // target patch: 8 rows x 16 cols
+constexpr int BN = PH * PW;      // 128 targets per tile (TMEM columns)
+constexpr int BK = 64;           // bf16 channels per smem stage row (128 bytes, SWIZZLE_128B)
+constexpr int UMMA_K = 16;
+constexpr int MAX_KB = 4;        // Kp <= 256
+constexpr int NSTAGE = 4;        // B ring depth
+constexpr int NACC = 4;          // TMEM accumulator buffers (4 x 128 columns)
+constexpr int A_TILE_BYTES = BM * BK * 2;  // 16 KB
+constexpr int B_TILE_BYTES = BN * BK * 2;  // 16 KB
+constexpr int STG_BYTES = 4096;            // one staged store box per warp
+constexpr int NUM_EPI_WARPS = 4;
+constexpr int THREADS = 32 * (2 + NUM_EPI_WARPS);
+
+struct SmemLayout {
+  // all tile buffers 1024-byte aligned (SWIZZLE_128B atoms)
+  static constexpr int a_off = 0;                                        // [part][kb] tiles
+  static constexpr int b_off = a_off + 2 * MAX_KB * A_TILE_BYTES;        // 128 KB
+  static constexpr int stg_off = b_off + NSTAGE * B_TILE_BYTES;          // + 64 KB
+  static constexpr int bar_off = stg_off + NUM_EPI_WARPS * 2 * STG_BYTES;  // + 32 KB
+  static constexpr int total = bar_off + 256;
+};
+
+struct Params {
+  int B, C, H, W, Q;
+  int kblocks;      // Kp / 64
+  int parts;        // 1 (bf16) or 2 (bf16x3)
+  int levels;
+  int mtiles;       // ceil(Q / 128)
+  int pcols, prows; // patch grid
+  int groups;       // patch groups per (b, m-tile)
+  int patches_per_group;
+  int units;        // B * mtiles * groups
+  float scale;      // 1 / sqrt(C)
+  int direct_store; // debug: bypass the TMA stores
+  float* pyr[RCB_MAX_LEVELS];
+  int Hl[RCB_MAX_LEVELS], Wl[RCB_MAX_LEVELS], rs[RCB_MAX_LEVELS];
+  long long ps[RCB_MAX_LEVELS];
+};
+
+// ---- PTX wrappers ------------------------------------------------------------------------
+RCB_DEVINL void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+RCB_DEVINL void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+RCB_DEVINL void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+RCB_DEVINL bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug traps (the launch fails with an error) instead of hanging the GPU.
+RCB_DEVINL void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 8000000000LL) __trap();
+  }
+}
+RCB_DEVINL void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+RCB_DEVINL void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+RCB_DEVINL void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+RCB_DEVINL void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+RCB_DEVINL void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+RCB_DEVINL void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+RCB_DEVINL void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map),
+               "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+RCB_DEVINL void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+RCB_DEVINL void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+RCB_DEVINL void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+RCB_DEVINL void tmem_alloc(uint32_t slot_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+RCB_DEVINL void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 operands, fp32 accumulate
+RCB_DEVINL void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// mbarrier arrives when all previously issued tcgen05.mma of this thread have completed
+RCB_DEVINL void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+RCB_DEVINL void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor: rows of 128 bytes, 8-row groups 1024 bytes apart.
+RCB_DEVINL uint64_t make_smem_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);  // start address
+  d |= (uint64_t)0 << 16;                      // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;            // stride byte offset between 8-row groups
+  d |= (uint64_t)1 << 46;                      // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                      // SWIZZLE_128B
+  return d;
+}
+// kind::f16 instruction descriptor: fp32 accumulate, bf16 x bf16, both K-major, M=128, N=128
+__host__ __device__ constexpr uint32_t make_idesc() {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(BN >> 3) << 17) |
+         ((uint32_t)(BM >> 4) << 24);
+}
+
+// ---- operand packing -----------------------------------------------------------------------
+// in  [2 maps][B][C][Q] fp32 (two separate base pointers);  out [map][part][B][Q][Kp] bf16, zero padded to Kp.
+__global__ void __launch_bounds__(256)
+pack_operands_kernel(const float* __restrict__ f1, const float* __restrict__ f2, __nv_bfloat16* __restrict__ out,
+                     int B, int C, int Q, int Kp, int parts) {
+  __shared__ float tile[64][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  const int map = blockIdx.z / B, b = blockIdx.z % B;
+  const float* in = (map == 0 ? f1 : f2) + (long long)b * C * Q;
+  const int q0 = blockIdx.x * 32, c0 = blockIdx.y * 64;
+  for (int c = ty; c < 64; c += 8) {
+    const int cc = c0 + c, q = q0 + tx;
+    tile[c][tx] = (cc < C && q < Q) ? __ldg(in + (long long)cc * Q + q) : 0.f;
+  }
+  __syncthreads();
+  const long long part_stride = (long long)B * Q * Kp;
+  __nv_bfloat16* o = out + (long long)map * parts * part_stride + (long long)b * Q * Kp;
+  for (int i = ty; i < 32; i += 8) {
+    const int q = q0 + i;
+    if (q >= Q) continue;
+    const float x0 = tile[2 * tx][i], x1 = tile[2 * tx + 1][i];
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
+    __nv_bfloat162 hi;
+    hi.x = h0;
+    hi.y = h1;
+    __nv_bfloat162* dst = reinterpret_cast<__nv_bfloat162*>(o + (long long)q * Kp + c0) + tx;
+    *dst = hi;
+    if (parts > 1) {
+      __nv_bfloat162 lo;
+      lo.x = __float2bfloat16_rn(x0 - __bfloat162float(h0));
+      lo.y = __float2bfloat16_rn(x1 - __bfloat162float(h1));
+      *reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<__nv_bfloat16*>(dst) + part_stride) = lo;
+    }
+  }
+}
+
+// ---- main kernel -------------------------------------------------------------------------------
+struct UnitCoord {
+  int b, mt, p_begin, p_end;
+};
+RCB_DEVINL UnitCoord decode_unit(const Params& p, int u) {
+  UnitCoord c;
+  const int g = u % p.groups;
+  const int t = u / p.groups;
+  c.mt = t % p.mtiles;
+  c.b = t / p.mtiles;
+  const int npatch = p.pcols * p.prows;
+  c.p_begin = g * p.patches_per_group;
+  c.p_end = min(npatch, c.p_begin + p.patches_per_group);
+  return c;
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                const __grid_constant__ CUtensorMap map_l0, const __grid_constant__ CUtensorMap map_l1,
+                const Params p) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const uint32_t smem_base = smem_u32(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // barriers (8 bytes each)
+  const uint32_t bar0 = smem_base + SmemLayout::bar_off;
+  const uint32_t a_full = bar0, a_empty = bar0 + 8;
+  auto b_full = [&](int s) { return bar0 + 16 + 8 * s; };
+  auto b_empty = [&](int s) { return bar0 + 16 + 8 * NSTAGE + 8 * s; };
+  auto acc_full = [&](int s) { return bar0 + 16 + 16 * NSTAGE + 8 * s; };
+  auto acc_empty = [&](int s) { return bar0 + 16 + 16 * NSTAGE + 8 * NACC + 8 * s; };
+  const uint32_t tmem_slot = bar0 + 16 + 16 * NSTAGE + 16 * NACC;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + SmemLayout::bar_off + 16 +
+                                                                           16 * NSTAGE + 16 * NACC);
+
+  if (threadIdx.x == 0) {
+    mbar_init(a_full, 1);
+    mbar_init(a_empty, 1);
+    for (int s = 0; s < NSTAGE; ++s) {
+      mbar_init(b_full(s), 1);
+      mbar_init(b_empty(s), 1);
+    }
+    for (int s = 0; s < NACC; ++s) {
+      mbar_init(acc_full(s), 1);
+      mbar_init(acc_empty(s), NUM_EPI_WARPS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, NACC * BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // =============================== TMA producer ===============================
+    if (lane == 0) {
+      uint32_t it = 0;  // B stage counter
+      uint32_t nunit = 0;
+      for (int u = blockIdx.x; u < p.units; u += gridDim.x, ++nunit) {
+        const UnitCoord uc = decode_unit(p, u);
+        if (nunit > 0) mbar_wait(a_empty, (nunit - 1) & 1);  // previous unit's MMAs have drained A
+        mbar_expect_tx(a_full, (uint32_t)(p.parts * p.kblocks * A_TILE_BYTES));
+        for (int part = 0; part < p.parts; ++part)
+          for (int kb = 0; kb < p.kblocks; ++kb)
+            tma_load_3d(smem_base + SmemLayout::a_off + (part * MAX_KB + kb) * A_TILE_BYTES, &map_a, a_full, kb * BK,
+                        uc.mt * BM, part * p.B + uc.b);
+        for (int pi = uc.p_begin; pi < uc.p_end; ++pi) {
+          const int py = pi / p.pcols, px = pi % p.pcols;
+          for (int kb = 0; kb < p.kblocks; ++kb)
+            for (int part = 0; part < p.parts; ++part, ++it) {
+              const int s = it % NSTAGE;
+              mbar_wait(b_empty(s), ((it / NSTAGE) & 1) ^ 1);
+              mbar_expect_tx(b_full(s), B_TILE_BYTES);
+              tma_load_4d(smem_base + SmemLayout::b_off + s * B_TILE_BYTES, &map_b, b_full(s), kb * BK, px * PW,
+                          py * PH, part * p.B + uc.b);
+            }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer ===============================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc();
+      uint32_t it = 0, tile = 0, nunit = 0;
+      for (int u = blockIdx.x; u < p.units; u += gridDim.x, ++nunit) {
+        const UnitCoord uc = decode_unit(p, u);
+        mbar_wait(a_full, nunit & 1);
+        tc_fence_after();
+        for (int pi = uc.p_begin; pi < uc.p_end; ++pi, ++tile) {
+          const int buf = tile % NACC;
+          mbar_wait(acc_empty(buf), ((tile / NACC) & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + buf * BN;
+          uint32_t first = 1;
+          for (int kb = 0; kb < p.kblocks; ++kb)
+            for (int part = 0; part < p.parts; ++part, ++it) {
+              const int s = it % NSTAGE;
+              mbar_wait(b_full(s), (it / NSTAGE) & 1);
+              tc_fence_after();
+              const uint64_t bdesc = make_smem_desc(smem_base + SmemLayout::b_off + s * B_TILE_BYTES);
+              const uint64_t a_hi = make_smem_desc(smem_base + SmemLayout::a_off + (0 * MAX_KB + kb) * A_TILE_BYTES);
+              const uint64_t a_lo = make_smem_desc(smem_base + SmemLayout::a_off + (1 * MAX_KB + kb) * A_TILE_BYTES);
+#pragma unroll
+              for (int k = 0; k < BK / UMMA_K; ++k) {  // +32 bytes per K step inside the swizzled row
+                umma_bf16(d_tmem, a_hi + 2 * k, bdesc + 2 * k, idesc, first ? 0u : 1u);
+                first = 0;
+              }
+              if (part == 0 && p.parts > 1) {  // B_hi also meets A_lo
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k) umma_bf16(d_tmem, a_lo + 2 * k, bdesc + 2 * k, idesc, 1u);
+              }
+              umma_commit(b_empty(s));  // frees the B stage once these MMAs have read it
+            }
+          umma_commit(acc_full(buf));
+        }
+        umma_commit(a_empty);
+      }
+    }
+  } else {
+    // =============================== epilogue ===============================
+    const int ew = warp - 2;             // staging slot
+    const int lane_q = (warp & 3) * 32;  // TMEM lane quarter this warp may access
+    unsigned char* stg = smem + SmemLayout::stg_off + ew * 2 * STG_BYTES;
+    uint32_t nstore = 0;  // staged stores issued by this warp (buffer = nstore & 1)
+    uint32_t tile = 0;
+    for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
+      const UnitCoord uc = decode_unit(p, u);
+      const int q_w = uc.mt * BM + lane_q;  // first query of this warp
+      const int q = q_w + lane;
+      const bool q_ok = q < p.Q;
+      const long long bq = (long long)uc.b * p.Q + q;
+      for (int pi = uc.p_begin; pi < uc.p_end; ++pi, ++tile) {
+        const int py = pi / p.pcols, px = pi % p.pcols;
+        const int y0 = py * PH, x0 = px * PW;
+        const int buf = tile % NACC;
+        mbar_wait(acc_full(buf), (tile / NACC) & 1);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)lane_q << 16) + buf * BN;
+        float l1[4][8];
+#pragma unroll
+        for (int rp = 0; rp < 4; ++rp) {
+          float v[32];
+          tmem_ld32(taddr + rp * 32, v);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] *= p.scale;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) l1[rp][j] = ((v[2 * j] + v[2 * j + 1]) + (v[16 + 2 * j] + v[16 + 2 * j + 1])) * 0.25f;
+          const int yy = y0 + 2 * rp;
+          if (p.direct_store) {
+            if (q_ok) {
+              float* plane = p.pyr[0] + bq * p.ps[0];
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                const int y = yy + (i >> 4), x = x0 + (i & 15);
+                if (y < p.H && x < p.W) plane[(long long)y * p.rs[0] + x] = v[i];
+              }
+            }
+          } else if (yy < p.H && q_w < p.Q) {  // warp-uniform
+            unsigned char* sb = stg + (nstore & 1) * STG_BYTES;
+            if (lane == 0) tma_store_wait_read<1>();  // the store that used this buffer has been read out
+            __syncwarp();
+            // box [32 queries][2 rows][16 cols]: 64-byte rows, SWIZZLE_64B (16-byte chunk index bits 0-1 of
+            // every row are XORed with bits 1-2 of the row index = query & 3) -> 2-way bank conflicts only
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float4 c = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+              *reinterpret_cast<float4*>(sb + lane * 128 + ((j ^ (lane & 3)) << 4)) = c;
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_4d(&map_l0, smem_u32(sb), x0, yy, q_w, uc.b);
+              tma_store_commit();
+            }
+            ++nstore;
+          }
+        }
+        // all TMEM reads of this accumulator are done: hand it back to the MMA warp
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_empty(buf));
+
+        if (p.levels > 1) {
+          const int y1 = y0 >> 1, x1 = x0 >> 1;
+          if (p.direct_store) {
+            if (q_ok) {
+              float* plane = p.pyr[1] + bq * p.ps[1];
+#pragma unroll
+              for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                  if (y1 + r < p.Hl[1] && x1 + j < p.Wl[1]) plane[(long long)(y1 + r) * p.rs[1] + x1 + j] = l1[r][j];
+            }
+          } else if (y1 < p.Hl[1] && x1 < p.Wl[1] && q_w < p.Q) {
+            unsigned char* sb = stg + (nstore & 1) * STG_BYTES;
+            if (lane == 0) tma_store_wait_read<1>();
+            __syncwarp();
+            // box [32 queries][4 rows][8 cols]: 32-byte rows, SWIZZLE_32B (chunk bit 0 ^= bit 2 of the row
+            // index = query & 1)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float4 c = make_float4(l1[j >> 1][4 * (j & 1)], l1[j >> 1][4 * (j & 1) + 1], l1[j >> 1][4 * (j & 1) + 2],
+                                     l1[j >> 1][4 * (j & 1) + 3]);
+              *reinterpret_cast<float4*>(sb + lane * 128 + ((j ^ (lane & 1)) << 4)) = c;
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_4d(&map_l1, smem_u32(sb), x1, y1, q_w, uc.b);
+              tma_store_commit();
+            }
+            ++nstore;
+          }
+        }
+        if (p.levels > 2 && q_ok) {
+          float l2[2][4];
+#pragma unroll
+          for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              l2[r][j] = ((l1[2 * r][2 * j] + l1[2 * r][2 * j + 1]) + (l1[2 * r + 1][2 * j] + l1[2 * r + 1][2 * j + 1])) * 0.25f;
+          const int y2 = y0 >> 2, x2 = x0 >> 2;
+          float* plane = p.pyr[2] + bq * p.ps[2];
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            if (y2 + r < p.Hl[2]) {
+              float* row = plane + (long long)(y2 + r) * p.rs[2] + x2;
+              if (x2 + 3 < p.Wl[2]) {
+                *reinterpret_cast<float4*>(row) = make_float4(l2[r][0], l2[r][1], l2[r][2], l2[r][3]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  if (x2 + j < p.Wl[2]) row[j] = l2[r][j];
+              }
+            }
+          }
+          if (p.levels > 3) {
+            const float a = ((l2[0][0] + l2[0][1]) + (l2[1][0] + l2[1][1])) * 0.25f;
+            const float c = ((l2[0][2] + l2[0][3]) + (l2[1][2] + l2[1][3])) * 0.25f;
+            const int y3 = y0 >> 3, x3 = x0 >> 3;
+            if (y3 < p.Hl[3]) {
+              float* row = p.pyr[3] + bq * p.ps[3] + (long long)y3 * p.rs[3] + x3;
+              if (x3 + 1 < p.Wl[3]) *reinterpret_cast<float2*>(row) = make_float2(a, c);
+              else if (x3 < p.Wl[3]) row[0] = a;
+            }
+          }
+        }
+      }
+    }
+    if (lane == 0) tma_store_wait_all();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, NACC * BN);
+  }
+}
+
+// ---- host side -------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = []() -> PFN_cuTensorMapEncodeTiled_v12000 {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPointByVersion("cuTensorMapEncodeTiled", &f, 12000, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      return nullptr;
+    return reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(f);
+  }();
+  return fn;
+}
+
+static bool encode(CUtensorMap* m, CUtensorMapDataType dt, int rank, const void* base, const cuuint64_t* dims,
+                   const cuuint64_t* strides_bytes, const cuuint32_t* box, CUtensorMapSwizzle sw) {
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = encode_fn()(m, dt, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+}  // namespace tc
+
+static int padded_k(int C) { return (C + tc::BK - 1) / tc::BK * tc::BK; }
+
+size_t build_tc_workspace_bytes(int B, int C, int H, int W, int mode) {
+  const int parts = mode == RCB_BUILD_BF16X3 ? 2 : 1;
+  return (size_t)2 * parts * B * H * W * padded_k(C) * sizeof(__nv_bfloat16);
+}
+
+int launch_build_tc(const float* f1, const float* f2, void* const* pyr, const rcb_pyramid_layout& lay, int B,
+                    int C, int H, int W, int mode, void* ws, size_t ws_bytes, cudaStream_t s) {
+  using namespace tc;
+  if (lay.dtype != RCB_F32) return RCB_ERR_UNSUPPORTED;
+  const int Kp = padded_k(C);
+  if (Kp > MAX_KB * BK) return RCB_ERR_UNSUPPORTED;  // A tile must stay resident (C <= 256)
+  if (!encode_fn()) return RCB_ERR_NO_DEVICE;
+  const int parts = mode == RCB_BUILD_BF16X3 ? 2 : 1;
+  const size_t need = build_tc_workspace_bytes(B, C, H, W, mode);
+  if (!ws || ws_bytes < need || (reinterpret_cast<uintptr_t>(ws) & 127)) return RCB_ERR_WORKSPACE;
+  const int Q = H * W;
+
+  // 1. pack: fp32 NCHW -> bf16 hi/lo, K-major
+  __nv_bfloat16* packed = static_cast<__nv_bfloat16*>(ws);
+  {
+    dim3 grid((Q + 31) / 32, Kp / 64, 2 * B);
+    pack_operands_kernel<<<grid, 256, 0, s>>>(f1, f2, packed, B, C, Q, Kp, parts);
+    int st = launch_status();
+    if (st != RCB_OK) return st;
+  }
+  const __nv_bfloat16* a_pack = packed;
+  const __nv_bfloat16* b_pack = packed + (size_t)parts * B * Q * Kp;
+
+  // 2. tensor maps
+  CUtensorMap map_a, map_b, map_l0, map_l1;
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)Kp, (cuuint64_t)Q, (cuuint64_t)parts * B};
+    cuuint64_t str[2] = {(cuuint64_t)Kp * 2, (cuuint64_t)Q * Kp * 2};
+    cuuint32_t box[3] = {BK, BM, 1};
+    if (!encode(&map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, a_pack, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B))
+      return RCB_ERR_INVALID_ARGUMENT;
+  }
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)Kp, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)parts * B};
+    cuuint64_t str[3] = {(cuuint64_t)Kp * 2, (cuuint64_t)W * Kp * 2, (cuuint64_t)Q * Kp * 2};
+    cuuint32_t box[4] = {BK, PW, PH, 1};
+    if (!encode(&map_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, b_pack, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B))
+      return RCB_ERR_INVALID_ARGUMENT;
+  }
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)Q, (cuuint64_t)B};
+    cuuint64_t str[3] = {(cuuint64_t)lay.row_stride[0] * 4, (cuuint64_t)lay.plane_stride[0] * 4,
+                         (cuuint64_t)Q * lay.plane_stride[0] * 4};
+    cuuint32_t box[4] = {PW, 2, 32, 1};
+    if (!encode(&map_l0, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, pyr[0], dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B))
+      return RCB_ERR_INVALID_ARGUMENT;
+  }
+  if (lay.levels > 1) {
+    cuuint64_t dims[4] = {(cuuint64_t)lay.W[1], (cuuint64_t)lay.H[1], (cuuint64_t)Q, (cuuint64_t)B};
+    cuuint64_t str[3] = {(cuuint64_t)lay.row_stride[1] * 4, (cuuint64_t)lay.plane_stride[1] * 4,
+                         (cuuint64_t)Q * lay.plane_stride[1] * 4};
+    cuuint32_t box[4] = {PW / 2, 4, 32, 1};
+    if (!encode(&map_l1, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, pyr[1], dims, str, box, CU_TENSOR_MAP_SWIZZLE_32B))
+      return RCB_ERR_INVALID_ARGUMENT;
+  } else {
+    map_l1 = map_l0;
+  }
+
+  // 3. work decomposition: unit = (batch, 128-query tile, group of patches); A stays resident per unit
+  Params p{};
+  p.B = B; p.C = C; p.H = H; p.W = W; p.Q = Q;
+  p.kblocks = Kp / BK;
+  p.parts = parts;
+  p.levels = lay.levels;
+  p.mtiles = (Q + BM - 1) / BM;
+  p.pcols = (W + PW - 1) / PW;
+  p.prows = (H + PH - 1) / PH;
+  const int npatch = p.pcols * p.prows;
+  const int base_units = B * p.mtiles;
+  int groups = 1;
+  // aim for >= 3 units per SM so the static round-robin balances, but keep >= 4 patches per A load
+  while (groups < npatch && base_units * groups < 3 * kNumSMs && (npatch + groups) / (groups + 1) >= 4) ++groups;
+  p.patches_per_group = (npatch + groups - 1) / groups;
+  p.groups = (npatch + p.patches_per_group - 1) / p.patches_per_group;
+  p.units = base_units * p.groups;
+  p.scale = 1.0f / sqrtf((float)C);
+  const char* dbg = getenv("RCB_TC_DIRECT_STORE");
+  p.direct_store = (dbg && dbg[0] == '1') ? 1 : 0;
+  for (int l = 0; l < RCB_MAX_LEVELS; ++l) {
+    p.pyr[l] = l < lay.levels ? static_cast<float*>(pyr[l]) : nullptr;
+    p.Hl[l] = lay.H[l]; p.Wl[l] = lay.W[l]; p.rs[l] = lay.row_stride[l]; p.ps[l] = lay.plane_stride[l];
+  }
+
+  cudaError_t e = cudaFuncSetAttribute(build_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout::total);
+  if (e != cudaSuccess) return (int)e;
+  const int grid = p.units < kNumSMs ? p.units : kNumSMs;
+  build_tc_kernel<<<grid, THREADS, SmemLayout::total, s>>>(map_a, map_b, map_l0, map_l1, p);
+  return launch_status();
+}
+
 }  // namespace rcb
