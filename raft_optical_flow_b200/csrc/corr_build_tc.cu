@@ -38,7 +38,7 @@ constexpr int BN = PH * PW;      // 128 targets per tile (TMEM columns)
 constexpr int BK = 64;           // bf16 channels per smem stage row (128 bytes, SWIZZLE_128B)
 constexpr int UMMA_K = 16;
 constexpr int MAX_KB = 4;        // Kp <= 256
-constexpr int NSTAGE = 4;        // B ring depth
+constexpr int MAX_STAGE = 8;     // B ring depth is chosen at launch from the shared memory left over by A
 constexpr int NACC = 4;          // TMEM accumulator buffers (4 x 128 columns)
 constexpr int A_TILE_BYTES = BM * BK * 2;  // 16 KB
 constexpr int B_TILE_BYTES = BN * BK * 2;  // 16 KB
@@ -46,14 +46,14 @@ constexpr int STG_BYTES = 4096;            // one staged store box per warp
 constexpr int NUM_EPI_WARPS = 4;
 constexpr int THREADS = 32 * (2 + NUM_EPI_WARPS);
 
-struct SmemLayout {
-  // all tile buffers 1024-byte aligned (SWIZZLE_128B atoms)
-  static constexpr int a_off = 0;                                        // [part][kb] tiles
-  static constexpr int b_off = a_off + 2 * MAX_KB * A_TILE_BYTES;        // 128 KB
-  static constexpr int stg_off = b_off + NSTAGE * B_TILE_BYTES;          // + 64 KB
-  static constexpr int bar_off = stg_off + NUM_EPI_WARPS * 2 * STG_BYTES;  // + 32 KB
-  static constexpr int total = bar_off + 256;
-};
+// Dynamic shared memory (all tile buffers 1024-byte aligned for the swizzle atoms):
+//   [0, a_bytes)            resident A tiles, index part * kblocks + kb
+//   [b_off, +nstage*16 KB)  B ring
+//   [stg_off, +32 KB)       epilogue staging, 2 x 4 KB per warp
+//   [bar_off, +1 KB)        mbarriers + TMEM base slot
+constexpr int SMEM_BUDGET = 227 * 1024;
+constexpr int STG_TOTAL = NUM_EPI_WARPS * 2 * STG_BYTES;
+constexpr int BAR_BYTES = 1024;
 
 struct Params {
   int B, C, H, W, Q;
@@ -67,6 +67,8 @@ struct Params {
   int units;        // B * mtiles * groups
   float scale;      // 1 / sqrt(C)
   int direct_store; // debug: bypass the TMA stores
+  int nstage, b_off, stg_off, bar_off;  // shared memory carve-up (bytes)
+  int debug_skip;   // debug bitmask: 1 skip L0 TMA store issue, 2 skip L1 store, 4 skip L2/L3, 8 skip staging writes
   float* pyr[RCB_MAX_LEVELS];
   int Hl[RCB_MAX_LEVELS], Wl[RCB_MAX_LEVELS], rs[RCB_MAX_LEVELS];
   long long ps[RCB_MAX_LEVELS];
@@ -100,6 +102,17 @@ RCB_DEVINL void mbar_wait(uint32_t bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > 8000000000LL) __trap();
   }
+}
+// true on exactly one lane of a fully converged warp; keeps the surrounding values warp-uniform so the
+// compiler can hold descriptors in uniform registers instead of serialising over lanes
+RCB_DEVINL bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
 }
 RCB_DEVINL void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 RCB_DEVINL void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -245,15 +258,16 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   // barriers (8 bytes each)
-  const uint32_t bar0 = smem_base + SmemLayout::bar_off;
+  const uint32_t bar0 = smem_base + p.bar_off;
+  const int NSTAGE = p.nstage;
   const uint32_t a_full = bar0, a_empty = bar0 + 8;
   auto b_full = [&](int s) { return bar0 + 16 + 8 * s; };
-  auto b_empty = [&](int s) { return bar0 + 16 + 8 * NSTAGE + 8 * s; };
-  auto acc_full = [&](int s) { return bar0 + 16 + 16 * NSTAGE + 8 * s; };
-  auto acc_empty = [&](int s) { return bar0 + 16 + 16 * NSTAGE + 8 * NACC + 8 * s; };
-  const uint32_t tmem_slot = bar0 + 16 + 16 * NSTAGE + 16 * NACC;
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + SmemLayout::bar_off + 16 +
-                                                                           16 * NSTAGE + 16 * NACC);
+  auto b_empty = [&](int s) { return bar0 + 16 + 8 * MAX_STAGE + 8 * s; };
+  auto acc_full = [&](int s) { return bar0 + 16 + 16 * MAX_STAGE + 8 * s; };
+  auto acc_empty = [&](int s) { return bar0 + 16 + 16 * MAX_STAGE + 8 * NACC + 8 * s; };
+  const uint32_t tmem_slot = bar0 + 16 + 16 * MAX_STAGE + 16 * NACC;
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem + p.bar_off + 16 + 16 * MAX_STAGE + 16 * NACC);
 
   if (threadIdx.x == 0) {
     mbar_init(a_full, 1);
@@ -275,75 +289,97 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   if (warp == 0) {
-    // =============================== TMA producer ===============================
-    if (lane == 0) {
-      uint32_t it = 0;  // B stage counter
-      uint32_t nunit = 0;
-      for (int u = blockIdx.x; u < p.units; u += gridDim.x, ++nunit) {
-        const UnitCoord uc = decode_unit(p, u);
-        if (nunit > 0) mbar_wait(a_empty, (nunit - 1) & 1);  // previous unit's MMAs have drained A
+    // =============================== TMA producer (whole warp runs the loop, one elected lane issues) ====
+    int s = 0;           // B ring slot
+    uint32_t ph = 0;     // its phase
+    uint32_t nunit = 0;
+    for (int u = blockIdx.x; u < p.units; u += gridDim.x, ++nunit) {
+      const UnitCoord uc = decode_unit(p, u);
+      if (nunit > 0) mbar_wait(a_empty, (nunit - 1) & 1);  // previous unit's MMAs have drained A
+      if (elect_one()) {
         mbar_expect_tx(a_full, (uint32_t)(p.parts * p.kblocks * A_TILE_BYTES));
         for (int part = 0; part < p.parts; ++part)
           for (int kb = 0; kb < p.kblocks; ++kb)
-            tma_load_3d(smem_base + SmemLayout::a_off + (part * MAX_KB + kb) * A_TILE_BYTES, &map_a, a_full, kb * BK,
-                        uc.mt * BM, part * p.B + uc.b);
-        for (int pi = uc.p_begin; pi < uc.p_end; ++pi) {
-          const int py = pi / p.pcols, px = pi % p.pcols;
-          for (int kb = 0; kb < p.kblocks; ++kb)
-            for (int part = 0; part < p.parts; ++part, ++it) {
-              const int s = it % NSTAGE;
-              mbar_wait(b_empty(s), ((it / NSTAGE) & 1) ^ 1);
-              mbar_expect_tx(b_full(s), B_TILE_BYTES);
-              tma_load_4d(smem_base + SmemLayout::b_off + s * B_TILE_BYTES, &map_b, b_full(s), kb * BK, px * PW,
-                          py * PH, part * p.B + uc.b);
+            tma_load_3d(smem_base + (part * p.kblocks + kb) * A_TILE_BYTES, &map_a, a_full, kb * BK, uc.mt * BM,
+                        part * p.B + uc.b);
+      }
+      __syncwarp();
+      for (int pi = uc.p_begin; pi < uc.p_end; ++pi) {
+        const int py = pi / p.pcols, px = pi % p.pcols;
+        for (int kb = 0; kb < p.kblocks; ++kb)
+          for (int part = 0; part < p.parts; ++part) {
+            mbar_wait(b_empty(s), ph ^ 1);
+            if (elect_one()) {
+              if (p.debug_skip & 16) {
+                mbar_arrive(b_full(s));
+              } else {
+                mbar_expect_tx(b_full(s), B_TILE_BYTES);
+                tma_load_4d(smem_base + p.b_off + s * B_TILE_BYTES, &map_b, b_full(s), kb * BK, px * PW, py * PH,
+                            part * p.B + uc.b);
+              }
             }
-        }
+            __syncwarp();
+            if (++s == NSTAGE) { s = 0; ph ^= 1; }
+          }
       }
     }
   } else if (warp == 1) {
-    // =============================== MMA issuer ===============================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc();
-      uint32_t it = 0, tile = 0, nunit = 0;
-      for (int u = blockIdx.x; u < p.units; u += gridDim.x, ++nunit) {
-        const UnitCoord uc = decode_unit(p, u);
-        mbar_wait(a_full, nunit & 1);
+    // =============================== MMA issuer (whole warp runs the loop, one elected lane issues) ======
+    constexpr uint32_t idesc = make_idesc();
+    const uint64_t desc_base = make_smem_desc(0);  // everything but the start address
+    int s = 0;
+    uint32_t ph = 0, tile = 0, nunit = 0;
+    for (int u = blockIdx.x; u < p.units; u += gridDim.x, ++nunit) {
+      const UnitCoord uc = decode_unit(p, u);
+      mbar_wait(a_full, nunit & 1);
+      tc_fence_after();
+      for (int pi = uc.p_begin; pi < uc.p_end; ++pi, ++tile) {
+        const int buf = tile % NACC;
+        mbar_wait(acc_empty(buf), ((tile / NACC) & 1) ^ 1);
         tc_fence_after();
-        for (int pi = uc.p_begin; pi < uc.p_end; ++pi, ++tile) {
-          const int buf = tile % NACC;
-          mbar_wait(acc_empty(buf), ((tile / NACC) & 1) ^ 1);
-          tc_fence_after();
-          const uint32_t d_tmem = tmem_base + buf * BN;
-          uint32_t first = 1;
-          for (int kb = 0; kb < p.kblocks; ++kb)
-            for (int part = 0; part < p.parts; ++part, ++it) {
-              const int s = it % NSTAGE;
-              mbar_wait(b_full(s), (it / NSTAGE) & 1);
-              tc_fence_after();
-              const uint64_t bdesc = make_smem_desc(smem_base + SmemLayout::b_off + s * B_TILE_BYTES);
-              const uint64_t a_hi = make_smem_desc(smem_base + SmemLayout::a_off + (0 * MAX_KB + kb) * A_TILE_BYTES);
-              const uint64_t a_lo = make_smem_desc(smem_base + SmemLayout::a_off + (1 * MAX_KB + kb) * A_TILE_BYTES);
+        const uint32_t d_tmem = tmem_base + buf * BN;
+        uint32_t acc = 0;
+        for (int kb = 0; kb < p.kblocks; ++kb) {
+          const uint64_t a_hi = desc_base | (uint64_t)(((smem_base + kb * A_TILE_BYTES) >> 4) & 0x3FFF);
+          const uint64_t a_lo = desc_base | (uint64_t)(((smem_base + (p.kblocks + kb) * A_TILE_BYTES) >> 4) & 0x3FFF);
+          for (int part = 0; part < p.parts; ++part) {
+            mbar_wait(b_full(s), ph);
+            tc_fence_after();
+            const uint64_t bdesc = desc_base | (uint64_t)(((smem_base + p.b_off + s * B_TILE_BYTES) >> 4) & 0x3FFF);
+            if (elect_one()) {
+              if (!(p.debug_skip & 32)) {
 #pragma unroll
-              for (int k = 0; k < BK / UMMA_K; ++k) {  // +32 bytes per K step inside the swizzled row
-                umma_bf16(d_tmem, a_hi + 2 * k, bdesc + 2 * k, idesc, first ? 0u : 1u);
-                first = 0;
-              }
-              if (part == 0 && p.parts > 1) {  // B_hi also meets A_lo
+                for (int k = 0; k < BK / UMMA_K; ++k) {  // +32 bytes per K step inside the swizzled row
+                  umma_bf16(d_tmem, a_hi + 2 * k, bdesc + 2 * k, idesc, acc);
+                  acc = 1;
+                }
+                if (part == 0 && p.parts > 1) {  // B_hi also meets A_lo
 #pragma unroll
-                for (int k = 0; k < BK / UMMA_K; ++k) umma_bf16(d_tmem, a_lo + 2 * k, bdesc + 2 * k, idesc, 1u);
+                  for (int k = 0; k < BK / UMMA_K; ++k) umma_bf16(d_tmem, a_lo + 2 * k, bdesc + 2 * k, idesc, 1u);
+                }
               }
-              umma_commit(b_empty(s));  // frees the B stage once these MMAs have read it
+              if (p.debug_skip & 128) mbar_arrive(b_empty(s));
+              else umma_commit(b_empty(s));  // frees the B stage once these MMAs have read it
             }
-          umma_commit(acc_full(buf));
+            acc = 1;
+            __syncwarp();
+            if (++s == NSTAGE) { s = 0; ph ^= 1; }
+          }
         }
-        umma_commit(a_empty);
+        if (elect_one()) {
+          if (p.debug_skip & 256) mbar_arrive(acc_full(buf));
+          else umma_commit(acc_full(buf));
+        }
+        __syncwarp();
       }
+      if (elect_one()) umma_commit(a_empty);
+      __syncwarp();
     }
   } else {
     // =============================== epilogue ===============================
     const int ew = warp - 2;             // staging slot
     const int lane_q = (warp & 3) * 32;  // TMEM lane quarter this warp may access
-    unsigned char* stg = smem + SmemLayout::stg_off + ew * 2 * STG_BYTES;
+    unsigned char* stg = smem + p.stg_off + ew * 2 * STG_BYTES;
     uint32_t nstore = 0;  // staged stores issued by this warp (buffer = nstore & 1)
     uint32_t tile = 0;
     for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
@@ -363,6 +399,10 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 #pragma unroll
         for (int rp = 0; rp < 4; ++rp) {
           float v[32];
+          if (p.debug_skip & 64) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = 0.f;
+          } else
           tmem_ld32(taddr + rp * 32, v);
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] *= p.scale;
@@ -382,6 +422,7 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             unsigned char* sb = stg + (nstore & 1) * STG_BYTES;
             if (lane == 0) tma_store_wait_read<1>();  // the store that used this buffer has been read out
             __syncwarp();
+            if (!(p.debug_skip & 8))
             // box [32 queries][2 rows][16 cols]: 64-byte rows, SWIZZLE_64B (16-byte chunk index bits 0-1 of
             // every row are XORed with bits 1-2 of the row index = query & 3) -> 2-way bank conflicts only
 #pragma unroll
@@ -391,7 +432,7 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             }
             fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) {
+            if (lane == 0 && !(p.debug_skip & 1)) {
               tma_store_4d(&map_l0, smem_u32(sb), x0, yy, q_w, uc.b);
               tma_store_commit();
             }
@@ -414,7 +455,7 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 for (int j = 0; j < 8; ++j)
                   if (y1 + r < p.Hl[1] && x1 + j < p.Wl[1]) plane[(long long)(y1 + r) * p.rs[1] + x1 + j] = l1[r][j];
             }
-          } else if (y1 < p.Hl[1] && x1 < p.Wl[1] && q_w < p.Q) {
+          } else if (y1 < p.Hl[1] && x1 < p.Wl[1] && q_w < p.Q && !(p.debug_skip & 2)) {
             unsigned char* sb = stg + (nstore & 1) * STG_BYTES;
             if (lane == 0) tma_store_wait_read<1>();
             __syncwarp();
@@ -435,7 +476,7 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             ++nstore;
           }
         }
-        if (p.levels > 2 && q_ok) {
+        if (p.levels > 2 && q_ok && !(p.debug_skip & 4)) {
           float l2[2][4];
 #pragma unroll
           for (int r = 0; r < 2; ++r)
@@ -590,15 +631,28 @@ int launch_build_tc(const float* f1, const float* f2, void* const* pyr, const rc
   p.scale = 1.0f / sqrtf((float)C);
   const char* dbg = getenv("RCB_TC_DIRECT_STORE");
   p.direct_store = (dbg && dbg[0] == '1') ? 1 : 0;
+  const char* skip = getenv("RCB_TC_DEBUG_SKIP");
+  p.debug_skip = skip ? atoi(skip) : 0;
   for (int l = 0; l < RCB_MAX_LEVELS; ++l) {
     p.pyr[l] = l < lay.levels ? static_cast<float*>(pyr[l]) : nullptr;
     p.Hl[l] = lay.H[l]; p.Wl[l] = lay.W[l]; p.rs[l] = lay.row_stride[l]; p.ps[l] = lay.plane_stride[l];
   }
 
-  cudaError_t e = cudaFuncSetAttribute(build_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout::total);
+  const int a_bytes = parts * p.kblocks * A_TILE_BYTES;
+  int nstage = (SMEM_BUDGET - BAR_BYTES - STG_TOTAL - a_bytes) / B_TILE_BYTES;
+  if (nstage > MAX_STAGE) nstage = MAX_STAGE;
+  if (const char* ns = getenv("RCB_TC_NSTAGE")) nstage = atoi(ns) < nstage ? atoi(ns) : nstage;
+  if (nstage < 2) return RCB_ERR_UNSUPPORTED;
+  p.nstage = nstage;
+  p.b_off = a_bytes;
+  p.stg_off = p.b_off + nstage * B_TILE_BYTES;
+  p.bar_off = p.stg_off + STG_TOTAL;
+  const int smem_total = p.bar_off + BAR_BYTES;
+
+  cudaError_t e = cudaFuncSetAttribute(build_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET);
   if (e != cudaSuccess) return (int)e;
   const int grid = p.units < kNumSMs ? p.units : kNumSMs;
-  build_tc_kernel<<<grid, THREADS, SmemLayout::total, s>>>(map_a, map_b, map_l0, map_l1, p);
+  build_tc_kernel<<<grid, THREADS, smem_total, s>>>(map_a, map_b, map_l0, map_l1, p);
   return launch_status();
 }
 

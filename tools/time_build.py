@@ -1,0 +1,40 @@
+"""Times rcb_corr_build (pack + main kernel) through the C ABI with preallocated buffers (no Python/torch
+allocation inside the timed loop), CUDA events on the launching stream.
+    python tools/time_build.py [--config cfg2] [--mode bf16x3] [--reps 20]"""
+import argparse, os, sys, time
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from bench import CONFIGS, SEED  # noqa: E402
+from raft_optical_flow_b200 import _cabi  # noqa: E402
+from raft_optical_flow_b200.corr import _Pyramid  # noqa: E402
+ap = argparse.ArgumentParser()
+ap.add_argument("--config", default="cfg2")
+ap.add_argument("--mode", default="bf16x3")
+ap.add_argument("--reps", type=int, default=20)
+a = ap.parse_args()
+B, C, H, W, r, L, iters, _ = CONFIGS[a.config]
+dev = torch.device("cuda:0")
+g = torch.Generator(device="cpu").manual_seed(SEED)
+f1 = (0.75 * torch.randn(B, C, H, W, generator=g)).to(dev)
+f2 = (0.75 * torch.randn(B, C, H, W, generator=g)).to(dev)
+lib = _cabi.lib()
+mode = _cabi.BUILD_MODES[a.mode]
+pyr = _Pyramid(B, H, W, L, dev)
+nws = lib.rcb_corr_build_workspace_bytes(B, C, H, W, mode)
+ws = torch.empty(max(nws, 16), dtype=torch.uint8, device=dev)
+s = torch.cuda.current_stream().cuda_stream
+def call():
+    _cabi.check(lib.rcb_corr_build(f1.data_ptr(), f2.data_ptr(), pyr.ptrs, B, C, H, W, L, mode, 0, ws.data_ptr(), nws, s), "build")
+for _ in range(3):
+    call()
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+t0 = time.perf_counter()
+e0.record()
+for _ in range(a.reps):
+    call()
+e1.record()
+t1 = time.perf_counter()
+torch.cuda.synchronize()
+print(f"{a.config} {a.mode} skip={os.environ.get('RCB_TC_DEBUG_SKIP','0')} nstage={os.environ.get('RCB_TC_NSTAGE','-')} "
+      f"build {e0.elapsed_time(e1) / a.reps * 1e3:.1f} us (host enqueue {1e6 * (t1 - t0) / a.reps:.1f} us/call)")
