@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define RCB_ABI_VERSION 1
+#define RCB_ABI_VERSION 2
 #define RCB_MAX_LEVELS 4 /* core/raft.py:46-53 fixes corr_levels = 4 */
 #define RCB_MAX_RADIUS 4 /* core/raft.py:47,53: radius 3 (small) / 4 (full) */
 
@@ -58,17 +58,23 @@ enum rcb_build_mode {
 
 /* Memory layout of the pyramid the build writes and the lookup reads.
  * Level l holds, for every query q in [0, B*H*W), one plane of H_l x W_l correlations
- * (H_l = H_{l-1}/2, W_l = W_{l-1}/2, floor -- core/corr.py:52-54).  Rows are padded to a multiple of
- * 16 bytes so that planes can be moved by TMA / 16-byte async copies:
- *   element (q, y, x) of level l lives at  q * plane_stride[l] + y * row_stride[l] + x   (elements).
- * Padding elements are never read as data and their contents are unspecified. */
+ * (H_l = H_{l-1}/2, W_l = W_{l-1}/2, floor -- core/corr.py:52-54).  A plane is stored as a row-major grid of
+ * 64-byte TILES of 4 rows x tile_w columns (tile_w = 4 for fp32, 8 for fp16): the (2r+2)^2 window the lookup
+ * gathers then touches ~10.6 DRAM atoms (64 B) per level instead of the ~16 a row-major plane costs, and the
+ * build writes 128..256 contiguous bytes per query and tile band.
+ *   element (q, y, x) of level l lives at (in elements)
+ *     q * plane_stride[l] + ((y / 4) * tiles_x[l] + x / tile_w) * (4 * tile_w) + (y % 4) * tile_w + x % tile_w
+ * Elements of edge tiles that lie outside H_l x W_l are padding: never read as data, contents unspecified. */
 typedef struct rcb_pyramid_layout {
   int32_t levels;
   int32_t dtype;                       /* enum rcb_dtype */
+  int32_t tile_w;                      /* columns per tile (tile = 4 rows x tile_w columns = 64 bytes) */
+  int32_t reserved;
   int32_t H[RCB_MAX_LEVELS];           /* logical rows of each level */
   int32_t W[RCB_MAX_LEVELS];           /* logical columns */
-  int32_t row_stride[RCB_MAX_LEVELS];  /* elements between rows (>= W, multiple of 16 bytes) */
-  int64_t plane_stride[RCB_MAX_LEVELS];/* elements between consecutive queries */
+  int32_t tiles_x[RCB_MAX_LEVELS];     /* tiles per tile-row: ceil(W / tile_w) */
+  int32_t tiles_y[RCB_MAX_LEVELS];     /* tile rows: ceil(H / 4) */
+  int64_t plane_stride[RCB_MAX_LEVELS];/* elements between consecutive queries = tiles_x * tiles_y * 4 * tile_w */
   int64_t level_bytes[RCB_MAX_LEVELS]; /* bytes to allocate for the level: B*H*W planes */
 } rcb_pyramid_layout;
 

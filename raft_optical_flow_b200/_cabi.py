@@ -9,6 +9,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libraftcorr_b200.so")
 
+ABI_VERSION = 2
 MAX_LEVELS = 4
 MAX_RADIUS = 4
 
@@ -25,9 +26,12 @@ class PyramidLayout(ctypes.Structure):
     _fields_ = [
         ("levels", ctypes.c_int32),
         ("dtype", ctypes.c_int32),
+        ("tile_w", ctypes.c_int32),
+        ("reserved", ctypes.c_int32),
         ("H", ctypes.c_int32 * MAX_LEVELS),
         ("W", ctypes.c_int32 * MAX_LEVELS),
-        ("row_stride", ctypes.c_int32 * MAX_LEVELS),
+        ("tiles_x", ctypes.c_int32 * MAX_LEVELS),
+        ("tiles_y", ctypes.c_int32 * MAX_LEVELS),
         ("plane_stride", ctypes.c_int64 * MAX_LEVELS),
         ("level_bytes", ctypes.c_int64 * MAX_LEVELS),
     ]
@@ -66,7 +70,7 @@ def lib():
             fn = getattr(handle, name)  # AttributeError if the library does not export the ABI
             fn.restype = res
             fn.argtypes = args
-        if handle.rcb_abi_version() != 1:
+        if handle.rcb_abi_version() != ABI_VERSION:
             raise RuntimeError("libraftcorr_b200.so ABI version mismatch")
         _lib = handle
     return _lib

@@ -50,11 +50,17 @@ class _Pyramid:
         self.bufs = [alloc(self.layout.level_bytes[l] // esize, dtype=tdtype, device=device) for l in range(levels)]
         self.ptrs = _cabi.ptr_array([b.data_ptr() for b in self.bufs])
 
-    def views(self):
-        """[B*H*W, 1, H_l, W_l] views, the shape of the reference's corr_pyramid entries (core/corr.py:44-54)."""
+    def level(self, l):
+        """Level l as a dense [B*H*W, 1, H_l, W_l] tensor, the shape of the reference's corr_pyramid entries
+        (core/corr.py:44-54).  The kernels keep planes as 64-byte tiles (rcb_pyramid_layout); this un-tiles a
+        copy with plain tensor ops and is meant for inspection/tests, not for the hot path."""
         lay, n = self.layout, self.B * self.H * self.W
-        return [self.bufs[l].as_strided((n, 1, lay.H[l], lay.W[l]), (lay.plane_stride[l], 0, lay.row_stride[l], 1))
-                for l in range(self.levels)]
+        ty, tx, tw = lay.tiles_y[l], lay.tiles_x[l], lay.tile_w
+        t = self.bufs[l].view(n, ty, tx, 4, tw).permute(0, 1, 3, 2, 4).reshape(n, ty * 4, tx * tw)
+        return t[:, :lay.H[l], :lay.W[l]].unsqueeze(1)
+
+    def views(self):
+        return [self.level(l) for l in range(self.levels)]
 
     def zero_(self):
         for b in self.bufs:
@@ -169,7 +175,12 @@ class CorrBlock:
         self._token = None
         if torch.is_grad_enabled() and (fmap1.requires_grad or fmap2.requires_grad):
             self._token = _BuildFn.apply(fmap1, fmap2, self._state)
-        self.corr_pyramid = self._state.pyr.views()
+
+    @property
+    def corr_pyramid(self):
+        """List of num_levels tensors [N*H*W, 1, H_i, W_i] like the reference attribute (core/corr.py:38,46-54);
+        nothing outside corr.py reads it in the reference.  Materialised on access from the tiled buffers."""
+        return self._state.pyr.views()
 
     def __call__(self, coords):
         if torch.is_grad_enabled() and (self._token is not None or coords.requires_grad):
@@ -183,10 +194,7 @@ class CorrBlock:
         B, C, H, W = f1.shape
         pyr = _Pyramid(B, H, W, 1, f1.device)
         _build(f1, f2, 1, _cabi.BUILD_MODES[mode or DEFAULT_MODE], pyr)
-        lay = pyr.layout
-        return pyr.bufs[0].as_strided((B, H, W, 1, H, W),
-                                      (H * W * lay.plane_stride[0], W * lay.plane_stride[0], lay.plane_stride[0], 0,
-                                       lay.row_stride[0], 1))
+        return pyr.level(0).reshape(B, H, W, 1, H, W)
 
 
 class AlternateCorrBlock:

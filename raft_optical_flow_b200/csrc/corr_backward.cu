@@ -2,7 +2,7 @@
 // reference core/corr.py:121,127):
 //   dF1[b,c,q] = sum_p dV0[b,q,p] * F2[b,c,p] / sqrt(C)        ("NT": both operands K(p)-contiguous)
 //   dF2[b,c,p] = sum_q dV0[b,q,p] * F1[b,c,q] / sqrt(C)        ("NN": B operand N(p)-contiguous)
-// fp32 SIMT tiles; dV0 is read in the level-0 pyramid layout (rows padded to 16 bytes).
+// fp32 SIMT tiles; dV0 is read in the level-0 pyramid layout (4x4 tiles).
 #include "rcb_common.cuh"
 
 namespace rcb {
@@ -15,12 +15,12 @@ constexpr int GM = 64, GN = 64, GK = 32, GT = 256;
 //   A: [M][K] row-major (lda = K)
 //   B_NT:  Bop(k,n) = Bm[n * ldb_plane + pad(k)]   (dV0[q=n][p=k])
 //   !B_NT: Bop(k,n) = Bm[k * ldb_plane + pad(n)]   (dV0[q=k][p=n])
-// pad(p) = (p / W) * rs + p % W maps a flattened target index to the padded plane.
+// pad(p) = tile_off(p / W, p % W) maps a flattened target index to the 4x4-tiled plane.
 template <bool B_NT>
 __global__ void __launch_bounds__(GT)
 contract_bwd_kernel(const float* __restrict__ A, const float* __restrict__ Bm, float* __restrict__ out, int M, int Nn,
                     int K, long long strideA, long long strideB, long long strideO, long long ldb_plane, int W,
-                    int rs, float scale) {
+                    int tiles_x, float scale) {
   __shared__ float As[GK][GM + 1];
   __shared__ float Bs[GK][GN + 1];
   const int tid = threadIdx.x;
@@ -29,7 +29,6 @@ contract_bwd_kernel(const float* __restrict__ A, const float* __restrict__ Bm, f
   A += b * strideA;
   Bm += b * strideB;
   out += b * strideO;
-  const bool dense = (rs == W);
   const int ty = tid / 16, tx = tid % 16;
   float acc[4][4] = {};
   for (int k0 = 0; k0 < K; k0 += GK) {
@@ -44,7 +43,7 @@ contract_bwd_kernel(const float* __restrict__ A, const float* __restrict__ Bm, f
         const int kk = i % GK, nn = i / GK;
         const int n = n0 + nn, k = k0 + kk;
         float v = 0.f;
-        if (n < Nn && k < K) v = __ldg(Bm + (long long)n * ldb_plane + (dense ? k : (k / W) * rs + k % W));
+        if (n < Nn && k < K) v = __ldg(Bm + (long long)n * ldb_plane + tile_off(k / W, k % W, tiles_x));
         Bs[kk][nn] = v;
       }
     } else {
@@ -52,7 +51,7 @@ contract_bwd_kernel(const float* __restrict__ A, const float* __restrict__ Bm, f
         const int nn = i % GN, kk = i / GN;
         const int n = n0 + nn, k = k0 + kk;
         float v = 0.f;
-        if (n < Nn && k < K) v = __ldg(Bm + (long long)k * ldb_plane + (dense ? n : (n / W) * rs + n % W));
+        if (n < Nn && k < K) v = __ldg(Bm + (long long)k * ldb_plane + tile_off(n / W, n % W, tiles_x));
         Bs[kk][nn] = v;
       }
     }
@@ -93,9 +92,9 @@ int launch_contract_backward(const float* f1, const float* f2, const float* dvol
   const long long sF = (long long)C * Q, sV = (long long)Q * lay.plane_stride[0];
   dim3 grid((Q + GN - 1) / GN, (C + GM - 1) / GM, B);
   contract_bwd_kernel<true><<<grid, GT, 0, s>>>(f2, dvol0, df1, C, Q, Q, sF, sV, sF, lay.plane_stride[0], W,
-                                                lay.row_stride[0], scale);
+                                                lay.tiles_x[0], scale);
   contract_bwd_kernel<false><<<grid, GT, 0, s>>>(f1, dvol0, df2, C, Q, Q, sF, sV, sF, lay.plane_stride[0], W,
-                                                 lay.row_stride[0], scale);
+                                                 lay.tiles_x[0], scale);
   return launch_status();
 }
 

@@ -18,7 +18,7 @@ constexpr int THREADS = 256;
 // tiles are loaded with coalesced row reads and need no transpose.
 __global__ void __launch_bounds__(THREADS)
 build_simt_kernel(const float* __restrict__ f1, const float* __restrict__ f2, float* __restrict__ v0, int C, int Q,
-                  int W, int row_stride, long long plane_stride, float divisor) {
+                  int W, int tiles_x, long long plane_stride, float divisor) {
   __shared__ __align__(16) float As[2][BK][BM];
   __shared__ __align__(16) float Bs[2][BK][BN];
   const int tid = threadIdx.x;
@@ -93,7 +93,7 @@ build_simt_kernel(const float* __restrict__ f1, const float* __restrict__ f2, fl
     }
   }
 
-  const bool dense_rows = (row_stride == W) && vec;
+  const bool chunked = (W & 3) == 0;  // 4 consecutive targets = one 16-byte tile row
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int q = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
@@ -104,14 +104,14 @@ build_simt_kernel(const float* __restrict__ f1, const float* __restrict__ f2, fl
       const int p = n0 + jh * 64 + tx * 4;
       float4 v = make_float4(acc[i][jh * 4 + 0] / divisor, acc[i][jh * 4 + 1] / divisor,
                              acc[i][jh * 4 + 2] / divisor, acc[i][jh * 4 + 3] / divisor);
-      if (dense_rows && p + 3 < Q) {
-        *reinterpret_cast<float4*>(plane + p) = v;
+      if (chunked && p + 3 < Q) {
+        *reinterpret_cast<float4*>(plane + tile_off(p / W, p % W, tiles_x)) = v;
       } else {
         const float vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int pe = p + e;
-          if (pe < Q) plane[(long long)(pe / W) * row_stride + (pe % W)] = vv[e];
+          if (pe < Q) plane[tile_off(pe / W, pe % W, tiles_x)] = vv[e];
         }
       }
     }
@@ -121,17 +121,18 @@ build_simt_kernel(const float* __restrict__ f1, const float* __restrict__ f2, fl
 // 2x2 floor-mode mean of every plane of one level (core/corr.py:53).
 __global__ void __launch_bounds__(256)
 pool_level_kernel(const float* __restrict__ in, float* __restrict__ out, long long total, int Ho, int Wo,
-                  int rs_in, long long ps_in, int rs_out, long long ps_out) {
+                  int tx_in, long long ps_in, int tx_out, long long ps_out) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int x = (int)(i % Wo);
     const long long t = i / Wo;
     const int y = (int)(t % Ho);
     const long long plane = t / Ho;
-    const float* s = in + plane * ps_in + (long long)(2 * y) * rs_in + 2 * x;
+    // (2y, 2x), (2y, 2x+1) share a tile row; row 2y+1 is the next 16-byte row of the same tile
+    const float* s = in + plane * ps_in + tile_off(2 * y, 2 * x, tx_in);
     const float2 r0 = *reinterpret_cast<const float2*>(s);
-    const float2 r1 = *reinterpret_cast<const float2*>(s + rs_in);
-    out[plane * ps_out + (long long)y * rs_out + x] = ((r0.x + r0.y) + (r1.x + r1.y)) * 0.25f;
+    const float2 r1 = *reinterpret_cast<const float2*>(s + 4);
+    out[plane * ps_out + tile_off(y, x, tx_out)] = ((r0.x + r0.y) + (r1.x + r1.y)) * 0.25f;
   }
 }
 
@@ -143,8 +144,8 @@ int launch_pool_levels(void* const* pyr, const rcb_pyramid_layout& lay, int B, i
     const long long want = (total + 255) / 256;
     const unsigned grid = (unsigned)(want < (long long)kNumSMs * 16 ? want : (long long)kNumSMs * 16);
     pool_level_kernel<<<grid, 256, 0, s>>>(static_cast<const float*>(pyr[l - 1]), static_cast<float*>(pyr[l]), total,
-                                           lay.H[l], lay.W[l], lay.row_stride[l - 1], lay.plane_stride[l - 1],
-                                           lay.row_stride[l], lay.plane_stride[l]);
+                                           lay.H[l], lay.W[l], lay.tiles_x[l - 1], lay.plane_stride[l - 1],
+                                           lay.tiles_x[l], lay.plane_stride[l]);
   }
   return launch_status();
 }
@@ -154,7 +155,7 @@ int launch_build_simt(const float* f1, const float* f2, void* const* pyr, const 
   if (lay.dtype != RCB_F32) return RCB_ERR_UNSUPPORTED;
   const int Q = H * W;
   dim3 grid((Q + BN - 1) / BN, (Q + BM - 1) / BM, B);
-  build_simt_kernel<<<grid, THREADS, 0, s>>>(f1, f2, static_cast<float*>(pyr[0]), C, Q, W, lay.row_stride[0],
+  build_simt_kernel<<<grid, THREADS, 0, s>>>(f1, f2, static_cast<float*>(pyr[0]), C, Q, W, lay.tiles_x[0],
                                              lay.plane_stride[0], sqrtf((float)C));
   int st = launch_status();
   if (st != RCB_OK) return st;
@@ -167,20 +168,20 @@ int launch_build_simt(const float* f1, const float* f2, void* const* pyr, const 
 // dfine[2y+dy, 2x+dx] += dcoarse[y, x] / 4 ; rows/cols dropped by the floor receive nothing.
 __global__ void __launch_bounds__(256)
 pool_backward_kernel(const float* __restrict__ dcoarse, float* __restrict__ dfine, long long total, int Hc, int Wc,
-                     int rs_c, long long ps_c, int rs_f, long long ps_f) {
+                     int tx_c, long long ps_c, int tx_f, long long ps_f) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int x = (int)(i % Wc);
     const long long t = i / Wc;
     const int y = (int)(t % Hc);
     const long long plane = t / Hc;
-    const float g = dcoarse[plane * ps_c + (long long)y * rs_c + x] * 0.25f;
-    float* f = dfine + plane * ps_f + (long long)(2 * y) * rs_f + 2 * x;
+    const float g = dcoarse[plane * ps_c + tile_off(y, x, tx_c)] * 0.25f;
+    float* f = dfine + plane * ps_f + tile_off(2 * y, 2 * x, tx_f);
     float2 r0 = *reinterpret_cast<float2*>(f);
-    float2 r1 = *reinterpret_cast<float2*>(f + rs_f);
+    float2 r1 = *reinterpret_cast<float2*>(f + 4);
     r0.x += g; r0.y += g; r1.x += g; r1.y += g;
     *reinterpret_cast<float2*>(f) = r0;
-    *reinterpret_cast<float2*>(f + rs_f) = r1;
+    *reinterpret_cast<float2*>(f + 4) = r1;
   }
 }
 
@@ -191,8 +192,8 @@ int launch_pool_backward(float* const* dpyr, const rcb_pyramid_layout& lay, int 
     if (total == 0) continue;
     const long long want = (total + 255) / 256;
     const unsigned grid = (unsigned)(want < (long long)kNumSMs * 16 ? want : (long long)kNumSMs * 16);
-    pool_backward_kernel<<<grid, 256, 0, s>>>(dpyr[l], dpyr[l - 1], total, lay.H[l], lay.W[l], lay.row_stride[l],
-                                              lay.plane_stride[l], lay.row_stride[l - 1], lay.plane_stride[l - 1]);
+    pool_backward_kernel<<<grid, 256, 0, s>>>(dpyr[l], dpyr[l - 1], total, lay.H[l], lay.W[l], lay.tiles_x[l],
+                                              lay.plane_stride[l], lay.tiles_x[l - 1], lay.plane_stride[l - 1]);
   }
   return launch_status();
 }

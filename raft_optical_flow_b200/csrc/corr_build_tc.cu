@@ -15,13 +15,15 @@
 //                 stream through a 4-stage mbarrier ring.
 //     warp 1      MMA issuer: tcgen05.mma.cta_group::1.kind::f16, M=128, N=128, K=16, SWIZZLE_128B K-major
 //                 smem descriptors, fp32 accumulators in TMEM, 4 accumulator buffers (512 columns).
-//     warps 2-5   epilogue: tcgen05.ld (lane = query, 32 columns = 2 patch rows x 16 targets), scale by
-//                 1/sqrt(C); level 0 goes through a swizzled staging buffer and a 4-D TMA store (the
-//                 store clips rows/cols/queries outside the tensor); levels 1-3 are 2x2 means formed in
-//                 registers from the same accumulator values -- the patch is 8x8-aligned, so all three
-//                 pooled levels are tile-local; floor-mode dropping of odd rows/cols falls out of the
-//                 store clipping (level k cell j is valid iff j < floor(H_{k-1}/2)).  Level 1 is TMA-stored,
-//                 levels 2/3 (6% / 1.5% of the bytes) are written with 16/8-byte global stores.
+//     warps 2-5   epilogue: tcgen05.ld (lane = query, 64 columns = 4 patch rows x 16 targets = one band of four
+//                 4x4 pyramid tiles = 256 contiguous bytes per query), scale by 1/sqrt(C); level 0 leaves
+//                 through a SWIZZLE_128B staging box and 4-D TMA stores of [32 queries][128 B] (the store
+//                 clips tile columns / tile rows / queries outside the tensor); levels 1-3 are 2x2 means
+//                 formed in registers from the same accumulator values -- the patch is 8x8-aligned, so all
+//                 three pooled levels are patch-local; floor-mode dropping of odd rows/cols needs no code:
+//                 a level-k cell computed from a dropped row/col is itself outside H_k x W_k, i.e. tile
+//                 padding or a clipped tile.  Level 1 is TMA-stored, levels 2/3 (6% / 1.5% of the bytes)
+//                 are written with 32/8-byte global stores.
 #include <cudaTypedefs.h>
 
 #include <cstdlib>
@@ -70,7 +72,7 @@ struct Params {
   int nstage, b_off, stg_off, bar_off;  // shared memory carve-up (bytes)
   int debug_skip;   // debug bitmask: 1 skip L0 TMA store issue, 2 skip L1 store, 4 skip L2/L3, 8 skip staging writes
   float* pyr[RCB_MAX_LEVELS];
-  int Hl[RCB_MAX_LEVELS], Wl[RCB_MAX_LEVELS], rs[RCB_MAX_LEVELS];
+  int Hl[RCB_MAX_LEVELS], Wl[RCB_MAX_LEVELS], tx[RCB_MAX_LEVELS];  // level sizes, tiles per tile row
   long long ps[RCB_MAX_LEVELS];
 };
 
@@ -397,46 +399,66 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         const uint32_t taddr = tmem_base + ((uint32_t)lane_q << 16) + buf * BN;
         float l1[4][8];
 #pragma unroll
-        for (int rp = 0; rp < 4; ++rp) {
-          float v[32];
+        for (int band = 0; band < 2; ++band) {  // 4 patch rows = one row of 4x4 tiles
+          float va[32], vb[32];                 // rows 4*band + {0,1} and + {2,3}, 16 columns each
           if (p.debug_skip & 64) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = 0.f;
-          } else
-          tmem_ld32(taddr + rp * 32, v);
+            for (int i = 0; i < 32; ++i) va[i] = vb[i] = 0.f;
+          } else {
+            tmem_ld32(taddr + band * 64, va);
+            tmem_ld32(taddr + band * 64 + 32, vb);
+          }
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] *= p.scale;
+          for (int i = 0; i < 32; ++i) {
+            va[i] *= p.scale;
+            vb[i] *= p.scale;
+          }
 #pragma unroll
-          for (int j = 0; j < 8; ++j) l1[rp][j] = ((v[2 * j] + v[2 * j + 1]) + (v[16 + 2 * j] + v[16 + 2 * j + 1])) * 0.25f;
-          const int yy = y0 + 2 * rp;
+          for (int j = 0; j < 8; ++j) {
+            l1[2 * band][j] = ((va[2 * j] + va[2 * j + 1]) + (va[16 + 2 * j] + va[16 + 2 * j + 1])) * 0.25f;
+            l1[2 * band + 1][j] = ((vb[2 * j] + vb[2 * j + 1]) + (vb[16 + 2 * j] + vb[16 + 2 * j + 1])) * 0.25f;
+          }
+          const int yy = y0 + 4 * band;
           if (p.direct_store) {
             if (q_ok) {
               float* plane = p.pyr[0] + bq * p.ps[0];
 #pragma unroll
               for (int i = 0; i < 32; ++i) {
-                const int y = yy + (i >> 4), x = x0 + (i & 15);
-                if (y < p.H && x < p.W) plane[(long long)y * p.rs[0] + x] = v[i];
+                const int x = x0 + (i & 15);
+                if (x < p.W) {
+                  if (yy + (i >> 4) < p.H) plane[tile_off(yy + (i >> 4), x, p.tx[0])] = va[i];
+                  if (yy + 2 + (i >> 4) < p.H) plane[tile_off(yy + 2 + (i >> 4), x, p.tx[0])] = vb[i];
+                }
               }
             }
           } else if (yy < p.H && q_w < p.Q) {  // warp-uniform
-            unsigned char* sb = stg + (nstore & 1) * STG_BYTES;
-            if (lane == 0) tma_store_wait_read<1>();  // the store that used this buffer has been read out
-            __syncwarp();
-            if (!(p.debug_skip & 8))
-            // box [32 queries][2 rows][16 cols]: 64-byte rows, SWIZZLE_64B (16-byte chunk index bits 0-1 of
-            // every row are XORed with bits 1-2 of the row index = query & 3) -> 2-way bank conflicts only
+            // The band's 4 tiles are 256 contiguous bytes per query; they leave as two 128-byte halves
+            // (2 tiles each) through a SWIZZLE_128B staging box [32 queries][128 B]: conflict-free st.shared.
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float4 c = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-              *reinterpret_cast<float4*>(sb + lane * 128 + ((j ^ (lane & 3)) << 4)) = c;
+            for (int half = 0; half < 2; ++half) {
+              if (x0 + 8 * half >= p.W) break;  // warp-uniform: these tiles do not exist
+              unsigned char* sb = stg + (nstore & 1) * STG_BYTES;
+              if (lane == 0) tma_store_wait_read<1>();  // the store that used this buffer has been read out
+              __syncwarp();
+              if (!(p.debug_skip & 8)) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {  // chunk c = tile (c >> 2) of this half, tile row (c & 3)
+                  const int col = 8 * half + 4 * (c >> 2);
+                  const int r = c & 3;
+                  const float* src = (r < 2) ? va : vb;
+                  const int o = (r & 1) * 16 + col;
+                  *reinterpret_cast<float4*>(sb + lane * 128 + ((c ^ (lane & 7)) << 4)) =
+                      make_float4(src[o], src[o + 1], src[o + 2], src[o + 3]);
+                }
+              }
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0 && !(p.debug_skip & 1)) {
+                tma_store_4d(&map_l0, smem_u32(sb), ((x0 >> 2) + 2 * half) * 16, (yy >> 2), q_w, uc.b);
+                tma_store_commit();
+              }
+              ++nstore;
             }
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0 && !(p.debug_skip & 1)) {
-              tma_store_4d(&map_l0, smem_u32(sb), x0, yy, q_w, uc.b);
-              tma_store_commit();
-            }
-            ++nstore;
           }
         }
         // all TMEM reads of this accumulator are done: hand it back to the MMA warp
@@ -445,7 +467,7 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         if (lane == 0) mbar_arrive(acc_empty(buf));
 
         if (p.levels > 1) {
-          const int y1 = y0 >> 1, x1 = x0 >> 1;
+          const int y1 = y0 >> 1, x1 = x0 >> 1;  // 4 rows x 8 cols = 2 tiles = 128 contiguous bytes per query
           if (p.direct_store) {
             if (q_ok) {
               float* plane = p.pyr[1] + bq * p.ps[1];
@@ -453,24 +475,22 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
               for (int r = 0; r < 4; ++r)
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
-                  if (y1 + r < p.Hl[1] && x1 + j < p.Wl[1]) plane[(long long)(y1 + r) * p.rs[1] + x1 + j] = l1[r][j];
+                  if (y1 + r < p.Hl[1] && x1 + j < p.Wl[1]) plane[tile_off(y1 + r, x1 + j, p.tx[1])] = l1[r][j];
             }
           } else if (y1 < p.Hl[1] && x1 < p.Wl[1] && q_w < p.Q && !(p.debug_skip & 2)) {
             unsigned char* sb = stg + (nstore & 1) * STG_BYTES;
             if (lane == 0) tma_store_wait_read<1>();
             __syncwarp();
-            // box [32 queries][4 rows][8 cols]: 32-byte rows, SWIZZLE_32B (chunk bit 0 ^= bit 2 of the row
-            // index = query & 1)
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float4 c = make_float4(l1[j >> 1][4 * (j & 1)], l1[j >> 1][4 * (j & 1) + 1], l1[j >> 1][4 * (j & 1) + 2],
-                                     l1[j >> 1][4 * (j & 1) + 3]);
-              *reinterpret_cast<float4*>(sb + lane * 128 + ((j ^ (lane & 1)) << 4)) = c;
+            for (int c = 0; c < 8; ++c) {  // chunk c = tile (c >> 2), tile row (c & 3)
+              const int r = c & 3, col = 4 * (c >> 2);
+              *reinterpret_cast<float4*>(sb + lane * 128 + ((c ^ (lane & 7)) << 4)) =
+                  make_float4(l1[r][col], l1[r][col + 1], l1[r][col + 2], l1[r][col + 3]);
             }
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
-              tma_store_4d(&map_l1, smem_u32(sb), x1, y1, q_w, uc.b);
+              tma_store_4d(&map_l1, smem_u32(sb), (x1 >> 2) * 16, (y1 >> 2), q_w, uc.b);
               tma_store_commit();
             }
             ++nstore;
@@ -483,30 +503,19 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 #pragma unroll
             for (int j = 0; j < 4; ++j)
               l2[r][j] = ((l1[2 * r][2 * j] + l1[2 * r][2 * j + 1]) + (l1[2 * r + 1][2 * j] + l1[2 * r + 1][2 * j + 1])) * 0.25f;
+          // level 2: 2 rows x 4 cols = two adjacent 16-byte rows of one tile (y2 is even, x2 a multiple of 4)
           const int y2 = y0 >> 2, x2 = x0 >> 2;
-          float* plane = p.pyr[2] + bq * p.ps[2];
-#pragma unroll
-          for (int r = 0; r < 2; ++r) {
-            if (y2 + r < p.Hl[2]) {
-              float* row = plane + (long long)(y2 + r) * p.rs[2] + x2;
-              if (x2 + 3 < p.Wl[2]) {
-                *reinterpret_cast<float4*>(row) = make_float4(l2[r][0], l2[r][1], l2[r][2], l2[r][3]);
-              } else {
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                  if (x2 + j < p.Wl[2]) row[j] = l2[r][j];
-              }
-            }
+          if (y2 < p.Hl[2] && x2 < p.Wl[2]) {
+            float* t2 = p.pyr[2] + bq * p.ps[2] + tile_off(y2, x2, p.tx[2]);
+            *reinterpret_cast<float4*>(t2) = make_float4(l2[0][0], l2[0][1], l2[0][2], l2[0][3]);
+            *reinterpret_cast<float4*>(t2 + 4) = make_float4(l2[1][0], l2[1][1], l2[1][2], l2[1][3]);
           }
           if (p.levels > 3) {
             const float a = ((l2[0][0] + l2[0][1]) + (l2[1][0] + l2[1][1])) * 0.25f;
             const float c = ((l2[0][2] + l2[0][3]) + (l2[1][2] + l2[1][3])) * 0.25f;
-            const int y3 = y0 >> 3, x3 = x0 >> 3;
-            if (y3 < p.Hl[3]) {
-              float* row = p.pyr[3] + bq * p.ps[3] + (long long)y3 * p.rs[3] + x3;
-              if (x3 + 1 < p.Wl[3]) *reinterpret_cast<float2*>(row) = make_float2(a, c);
-              else if (x3 < p.Wl[3]) row[0] = a;
-            }
+            const int y3 = y0 >> 3, x3 = x0 >> 3;  // x3 is even: both values sit in one tile row
+            if (y3 < p.Hl[3] && x3 < p.Wl[3])
+              *reinterpret_cast<float2*>(p.pyr[3] + bq * p.ps[3] + tile_off(y3, x3, p.tx[3])) = make_float2(a, c);
           }
         }
       }
@@ -592,23 +601,19 @@ int launch_build_tc(const float* f1, const float* f2, void* const* pyr, const rc
     if (!encode(&map_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, b_pack, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B))
       return RCB_ERR_INVALID_ARGUMENT;
   }
-  {
-    cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)Q, (cuuint64_t)B};
-    cuuint64_t str[3] = {(cuuint64_t)lay.row_stride[0] * 4, (cuuint64_t)lay.plane_stride[0] * 4,
-                         (cuuint64_t)Q * lay.plane_stride[0] * 4};
-    cuuint32_t box[4] = {PW, 2, 32, 1};
-    if (!encode(&map_l0, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, pyr[0], dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B))
+  // stores: a level is viewed as [B][Q][tile rows][tiles_x * 16 floats]; one box = 2 tiles (128 B) x 32 queries
+  for (int l = 0; l < 2; ++l) {
+    CUtensorMap* m = l == 0 ? &map_l0 : &map_l1;
+    if (l >= lay.levels) {
+      *m = map_l0;
+      break;
+    }
+    cuuint64_t dims[4] = {(cuuint64_t)lay.tiles_x[l] * 16, (cuuint64_t)lay.tiles_y[l], (cuuint64_t)Q, (cuuint64_t)B};
+    cuuint64_t str[3] = {(cuuint64_t)lay.tiles_x[l] * 64, (cuuint64_t)lay.plane_stride[l] * 4,
+                         (cuuint64_t)Q * lay.plane_stride[l] * 4};
+    cuuint32_t box[4] = {32, 1, 32, 1};
+    if (!encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, pyr[l], dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B))
       return RCB_ERR_INVALID_ARGUMENT;
-  }
-  if (lay.levels > 1) {
-    cuuint64_t dims[4] = {(cuuint64_t)lay.W[1], (cuuint64_t)lay.H[1], (cuuint64_t)Q, (cuuint64_t)B};
-    cuuint64_t str[3] = {(cuuint64_t)lay.row_stride[1] * 4, (cuuint64_t)lay.plane_stride[1] * 4,
-                         (cuuint64_t)Q * lay.plane_stride[1] * 4};
-    cuuint32_t box[4] = {PW / 2, 4, 32, 1};
-    if (!encode(&map_l1, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, pyr[1], dims, str, box, CU_TENSOR_MAP_SWIZZLE_32B))
-      return RCB_ERR_INVALID_ARGUMENT;
-  } else {
-    map_l1 = map_l0;
   }
 
   // 3. work decomposition: unit = (batch, 128-query tile, group of patches); A stays resident per unit
@@ -635,7 +640,7 @@ int launch_build_tc(const float* f1, const float* f2, void* const* pyr, const rc
   p.debug_skip = skip ? atoi(skip) : 0;
   for (int l = 0; l < RCB_MAX_LEVELS; ++l) {
     p.pyr[l] = l < lay.levels ? static_cast<float*>(pyr[l]) : nullptr;
-    p.Hl[l] = lay.H[l]; p.Wl[l] = lay.W[l]; p.rs[l] = lay.row_stride[l]; p.ps[l] = lay.plane_stride[l];
+    p.Hl[l] = lay.H[l]; p.Wl[l] = lay.W[l]; p.tx[l] = lay.tiles_x[l]; p.ps[l] = lay.plane_stride[l];
   }
 
   const int a_bytes = parts * p.kblocks * A_TILE_BYTES;

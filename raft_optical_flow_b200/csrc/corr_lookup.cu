@@ -7,11 +7,13 @@
 //
 // Work decomposition
 //   CTA   = 32 consecutive query pixels in flattened (h, w) order (so every output channel is written
-//           as one 128-byte line), all levels.  128 threads.
+//           as one 128-byte line) of ONE level; 128 threads, ~21 KB of shared memory, so ~9 CTAs are
+//           resident per SM and their fetch / math / store phases overlap.
 //   fetch = all threads issue 16-byte cp.async (L2-only, zero-fill) for the aligned chunks that cover
 //           each window row; out-of-plane rows/chunks are zero-filled by the copy itself, which IS the
-//           zeros-padding of grid_sample.  4 consecutive lanes cover one 64-byte row segment.
-//   math  = warp l resamples level l; lane = query.  The window of a lane is read back with
+//           zeros-padding of grid_sample.  Planes are stored as 4x4 tiles of 64 bytes (one DRAM atom), so
+//           a (2r+2)^2 window touches ~3.25^2 atoms instead of ~1.6 per row.
+//   math  = lane = query, the 4 warps split the output rows.  The window of a lane is read back with
 //           conflict-free LDS.128 (per-query block stride is an odd number of 16-byte units), aligned
 //           with two select stages, separable bilinear weights (all (2r+1)^2 samples of one level share
 //           the same fractional offset because the window offsets are integers).
@@ -55,17 +57,19 @@ RCB_DEVINL LevelCoord level_coord(float cx, float cy, int l, int Hl, int Wl) {
 
 template <int R>
 __global__ void __launch_bounds__(LookupCfg<R>::THREADS)
-lookup_f32_kernel(PyramidDev pyr, const float* __restrict__ coords, float* __restrict__ out, int Q, int L,
-                  int qtiles) {
+lookup_f32_kernel(PyramidDev pyr, const float* __restrict__ coords, float* __restrict__ out, int Q, int L) {
   using Cfg = LookupCfg<R>;
   constexpr int RD = Cfg::RD, ROWS = Cfg::ROWS, NCH = Cfg::NCH, BLK16 = Cfg::BLK16, QT = Cfg::QT;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  float4* win = reinterpret_cast<float4*>(smem_raw);  // [L][QT][BLK16]
+  __shared__ float4 win[QT * BLK16];  // one level of 32 query windows, 16-byte chunks
   __shared__ float s_cx[QT], s_cy[QT];
 
   const int tid = threadIdx.x;
-  const int b = blockIdx.x / qtiles;
-  const int q0 = (blockIdx.x % qtiles) * QT;
+  const int l = blockIdx.y;
+  const int b = blockIdx.z;
+  const int q0 = blockIdx.x * QT;
+  const int Hl = pyr.H[l], Wl = pyr.W[l], tw = pyr.tiles_x[l];
+  const long long ps = pyr.plane_stride[l];
+  const float* __restrict__ base = static_cast<const float*>(pyr.ptr[l]);
 
   if (tid < QT) {
     const int q = q0 + tid;
@@ -80,71 +84,68 @@ lookup_f32_kernel(PyramidDev pyr, const float* __restrict__ coords, float* __res
   __syncthreads();
 
   // ---- fetch: zero-filling 16-byte async copies of every window row ------------------------
+  // 4 consecutive lanes cover the (up to) 64-byte span of one window row; chunks the window does not reach
+  // are not fetched at all.
   const long long q_base = (long long)b * Q + q0;
-#pragma unroll
-  for (int l = 0; l < RCB_MAX_LEVELS; ++l) {
-    if (l < L) {
-      const int Hl = pyr.H[l], Wl = pyr.W[l], rs = pyr.row_stride[l];
-      const long long ps = pyr.plane_stride[l];
-      const float* base = static_cast<const float*>(pyr.ptr[l]);
-      const uint32_t dst0 = smem_u32(win + (size_t)l * QT * BLK16);
-      for (int i = tid; i < QT * ROWS * NCH; i += Cfg::THREADS) {
-        const int c = i % NCH;
-        const int t = i / NCH;
-        const int j = t % ROWS;
-        const int q = t / ROWS;
-        const LevelCoord lc = level_coord<R>(s_cx[q], s_cy[q], l, Hl, Wl);
-        const int xa = lc.xs - (lc.xs & 3);  // 16-byte aligned start (may be negative)
-        const int y = lc.ys + j;
-        const int xc = xa + 4 * c;
-        const bool ok = (y >= 0) && (y < Hl) && (xc >= 0) && (xc < Wl);
-        const int nvalid = min(4, Wl - xc);
-        const float* src = ok ? base + (q_base + q) * ps + (long long)y * rs + xc : base;
-        cp_async16_zfill(dst0 + (uint32_t)((q * BLK16 + j * NCH + c) * 16), src, ok ? nvalid * 4 : 0);
-      }
-    }
+  const uint32_t dst0 = smem_u32(win);
+  for (int i = tid; i < QT * ROWS * NCH; i += Cfg::THREADS) {
+    const int c = i % NCH;
+    const int t = i / NCH;
+    const int j = t % ROWS;
+    const int q = t / ROWS;
+    const LevelCoord lc = level_coord<R>(s_cx[q], s_cy[q], l, Hl, Wl);
+    const int ph = lc.xs & 3;
+    if (4 * c >= ph + ROWS) continue;   // chunk lies beyond the last tap of this row
+    const int xa = lc.xs - ph;          // 16-byte aligned start (may be negative)
+    const int y = lc.ys + j;
+    const int xc = xa + 4 * c;
+    const bool ok = (y >= 0) && (y < Hl) && (xc >= 0) && (xc < Wl);
+    const int nvalid = min(4, Wl - xc);
+    // an aligned 4-float chunk of a row is exactly one 16-byte row of one 4x4 tile
+    const float* src = ok ? base + (q_base + q) * ps + tile_off(y, xc, tw) : base;
+    cp_async16_zfill(dst0 + (uint32_t)((q * BLK16 + j * NCH + c) * 16), src, ok ? nvalid * 4 : 0);
   }
   cp_async_commit();
   cp_async_wait<0>();
   __syncthreads();
 
-  // ---- math + store: warp = level, lane = query ----------------------------------------
-  const int lane = tid & 31;
+  // ---- math + store: lane = query, the 4 warps split the (2r+1) output rows ------------------
+  const int lane = tid & 31, warp = tid >> 5;
+  constexpr int NW = Cfg::THREADS / 32;
+  const int b_begin = (RD * warp) / NW, b_end = (RD * (warp + 1)) / NW;  // output rows (y offsets) of this warp
+  if (b_begin == b_end) return;
   const bool q_ok = q0 + lane < Q;
-  for (int l = tid >> 5; l < L; l += Cfg::THREADS / 32) {
-    const LevelCoord lc = level_coord<R>(s_cx[lane], s_cy[lane], l, pyr.H[l], pyr.W[l]);
-    const int p = lc.xs & 3;
-    const float fx = lc.fx, fy = lc.fy, gx = 1.0f - lc.fx, gy = 1.0f - lc.fy;
-    const float4* blk = win + ((size_t)l * QT + lane) * BLK16;
-    float* o = out + ((long long)b * L + l) * RD * RD * Q + q0 + lane;
-    float prev[RD];
+  const LevelCoord lc = level_coord<R>(s_cx[lane], s_cy[lane], l, Hl, Wl);
+  const int ph = lc.xs & 3;
+  const float fx = lc.fx, fy = lc.fy, gx = 1.0f - lc.fx, gy = 1.0f - lc.fy;
+  const float4* blk = win + lane * BLK16;
+  float* o = out + ((long long)b * L + l) * RD * RD * Q + q0 + lane;
+  float prev[RD];
+  for (int j = b_begin; j <= b_end; ++j) {  // input rows b_begin .. b_end
+    float wv[4 * NCH];
 #pragma unroll
-    for (int j = 0; j < ROWS; ++j) {
-      float wv[4 * NCH];
-#pragma unroll
-      for (int c = 0; c < NCH; ++c) {
-        const float4 v = blk[j * NCH + c];
-        wv[4 * c + 0] = v.x;
-        wv[4 * c + 1] = v.y;
-        wv[4 * c + 2] = v.z;
-        wv[4 * c + 3] = v.w;
-      }
-      float v1[ROWS + 2];
-#pragma unroll
-      for (int i = 0; i < ROWS + 2; ++i) v1[i] = (p & 1) ? wv[i + 1] : wv[i];
-      float s[ROWS];
-#pragma unroll
-      for (int i = 0; i < ROWS; ++i) s[i] = (p & 2) ? v1[i + 2] : v1[i];
-      float t[RD];
-#pragma unroll
-      for (int a = 0; a < RD; ++a) t[a] = gx * s[a] + fx * s[a + 1];
-      if (j > 0 && q_ok) {
-#pragma unroll
-        for (int a = 0; a < RD; ++a) o[(long long)(a * RD + (j - 1)) * Q] = gy * prev[a] + fy * t[a];
-      }
-#pragma unroll
-      for (int a = 0; a < RD; ++a) prev[a] = t[a];
+    for (int c = 0; c < NCH; ++c) {
+      const float4 v = blk[j * NCH + c];
+      wv[4 * c + 0] = v.x;
+      wv[4 * c + 1] = v.y;
+      wv[4 * c + 2] = v.z;
+      wv[4 * c + 3] = v.w;
     }
+    float v1[ROWS + 2];
+#pragma unroll
+    for (int i = 0; i < ROWS + 2; ++i) v1[i] = (ph & 1) ? wv[i + 1] : wv[i];
+    float s[ROWS];
+#pragma unroll
+    for (int i = 0; i < ROWS; ++i) s[i] = (ph & 2) ? v1[i + 2] : v1[i];
+    float t[RD];
+#pragma unroll
+    for (int a = 0; a < RD; ++a) t[a] = gx * s[a] + fx * s[a + 1];
+    if (j > b_begin && q_ok) {
+#pragma unroll
+      for (int a = 0; a < RD; ++a) o[(long long)(a * RD + (j - 1)) * Q] = gy * prev[a] + fy * t[a];
+    }
+#pragma unroll
+    for (int a = 0; a < RD; ++a) prev[a] = t[a];
   }
 }
 
@@ -153,28 +154,15 @@ static int launch_lookup_r(const PyramidDev& pd, const float* coords, float* out
                            cudaStream_t s) {
   using Cfg = LookupCfg<R>;
   const int Q = H * W;
-  const int qtiles = (Q + Cfg::QT - 1) / Cfg::QT;
-  const size_t smem = (size_t)L * Cfg::QT * Cfg::BLK16 * 16;
-  auto kern = lookup_f32_kernel<R>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return (int)e;
-  const long long nblk = (long long)B * qtiles;
-  if (nblk > 0x7fffffffLL) return RCB_ERR_INVALID_ARGUMENT;
-  kern<<<(unsigned)nblk, Cfg::THREADS, smem, s>>>(pd, coords, out, Q, L, qtiles);
+  dim3 grid((Q + Cfg::QT - 1) / Cfg::QT, L, B);
+  lookup_f32_kernel<R><<<grid, Cfg::THREADS, 0, s>>>(pd, coords, out, Q, L);
   return launch_status();
 }
 
 int launch_lookup(const void* const* pyr, const rcb_pyramid_layout& lay, const float* coords, float* out, int B,
                   int H, int W, int radius, cudaStream_t s) {
   if (lay.dtype != RCB_F32) return RCB_ERR_UNSUPPORTED;
-  PyramidDev pd;
-  for (int l = 0; l < RCB_MAX_LEVELS; ++l) {
-    pd.ptr[l] = l < lay.levels ? pyr[l] : nullptr;
-    pd.H[l] = lay.H[l];
-    pd.W[l] = lay.W[l];
-    pd.row_stride[l] = lay.row_stride[l];
-    pd.plane_stride[l] = lay.plane_stride[l];
-  }
+  const PyramidDev pd = make_pyramid_dev(pyr, lay);
   switch (radius) {
     case 1: return launch_lookup_r<1>(pd, coords, out, B, H, W, lay.levels, s);
     case 2: return launch_lookup_r<2>(pd, coords, out, B, H, W, lay.levels, s);
@@ -208,11 +196,10 @@ lookup_backward_kernel(PyramidDev pyr, PyramidDev dpyr, const float* __restrict_
   const float cy = __ldg(coords + ((long long)b * 2 + 1) * Q + q);
   float gx = 0.0f, gy = 0.0f;
   for (int l = 0; l < L; ++l) {
-    const int Hl = pyr.H[l], Wl = pyr.W[l], rs = pyr.row_stride[l];
+    const int Hl = pyr.H[l], Wl = pyr.W[l], tw = pyr.tiles_x[l];
     const float* plane = static_cast<const float*>(pyr.ptr[l]) + bq * pyr.plane_stride[l];
     float* dplane = want_dpyr ? static_cast<float*>(const_cast<void*>(dpyr.ptr[l])) + bq * dpyr.plane_stride[l]
                               : nullptr;
-    const int drs = dpyr.row_stride[l];
     const LevelCoord lc = level_coord<R>(cx, cy, l, Hl, Wl);
     const float fx = lc.fx, fy = lc.fy;
     const float inv = 1.0f / (float)(1 << l);
@@ -228,8 +215,9 @@ lookup_backward_kernel(PyramidDev pyr, PyramidDev dpyr, const float* __restrict_
       for (int k = 0; k < 4; ++k) {
         const int x = x0 + (k & 1), y = y0 + (k >> 1);
         if (x >= 0 && x < Wl && y >= 0 && y < Hl) {
-          if (want_dpyr) atomicAdd(dplane + (long long)y * drs + x, go * wgt[k]);
-          const float v = __ldg(plane + (long long)y * rs + x);
+          const long long off = tile_off(y, x, tw);
+          if (want_dpyr) atomicAdd(dplane + off, go * wgt[k]);
+          const float v = __ldg(plane + off);
           lgx += go * wdx[k] * v;
           lgy += go * wdy[k] * v;
         }
@@ -250,15 +238,8 @@ int launch_lookup_backward(const void* const* pyr, const rcb_pyramid_layout& lay
                            const float* grad_out, float* const* dpyr, float* dcoords, int B, int H, int W,
                            int radius, cudaStream_t s) {
   if (lay.dtype != RCB_F32) return RCB_ERR_UNSUPPORTED;
-  PyramidDev pd, dd;
-  for (int l = 0; l < RCB_MAX_LEVELS; ++l) {
-    pd.ptr[l] = l < lay.levels ? pyr[l] : nullptr;
-    dd.ptr[l] = (dpyr && l < lay.levels) ? dpyr[l] : nullptr;
-    pd.H[l] = dd.H[l] = lay.H[l];
-    pd.W[l] = dd.W[l] = lay.W[l];
-    pd.row_stride[l] = dd.row_stride[l] = lay.row_stride[l];
-    pd.plane_stride[l] = dd.plane_stride[l] = lay.plane_stride[l];
-  }
+  const PyramidDev pd = make_pyramid_dev(pyr, lay);
+  const PyramidDev dd = make_pyramid_dev(reinterpret_cast<const void* const*>(dpyr), lay);
   const long long nq = (long long)B * H * W;
   const unsigned grid = (unsigned)((nq + 3) / 4);
   switch (radius) {

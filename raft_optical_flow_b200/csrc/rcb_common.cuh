@@ -24,31 +24,51 @@ struct PyramidDev {
   const void* ptr[RCB_MAX_LEVELS];
   int H[RCB_MAX_LEVELS];
   int W[RCB_MAX_LEVELS];
-  int row_stride[RCB_MAX_LEVELS];
+  int tiles_x[RCB_MAX_LEVELS];
   long long plane_stride[RCB_MAX_LEVELS];
 };
+
+// Offset (in fp32 elements) of plane element (y, x) in the 4x4-tiled layout (see rcb_pyramid_layout).
+__host__ __device__ __forceinline__ long long tile_off(int y, int x, int tiles_x) {
+  return ((long long)((y >> 2) * tiles_x + (x >> 2)) << 4) + ((y & 3) << 2) + (x & 3);
+}
+
+inline PyramidDev make_pyramid_dev(const void* const* ptrs, const rcb_pyramid_layout& lay) {
+  PyramidDev pd;
+  for (int l = 0; l < RCB_MAX_LEVELS; ++l) {
+    pd.ptr[l] = (ptrs && l < lay.levels) ? ptrs[l] : nullptr;
+    pd.H[l] = lay.H[l];
+    pd.W[l] = lay.W[l];
+    pd.tiles_x[l] = lay.tiles_x[l];
+    pd.plane_stride[l] = lay.plane_stride[l];
+  }
+  return pd;
+}
 
 inline int fill_layout(int B, int H, int W, int levels, int dtype, rcb_pyramid_layout* lay) {
   if (!lay || B <= 0 || H <= 0 || W <= 0) return RCB_ERR_INVALID_ARGUMENT;
   if (levels < 1 || levels > RCB_MAX_LEVELS) return RCB_ERR_UNSUPPORTED;
   if (dtype != RCB_F32 && dtype != RCB_F16) return RCB_ERR_UNSUPPORTED;
   const int esize = dtype == RCB_F32 ? 4 : 2;
-  const int align_elems = 16 / esize;
+  const int tile_w = 16 / esize;  // 4 rows x tile_w columns = 64 bytes
   lay->levels = levels;
   lay->dtype = dtype;
+  lay->tile_w = tile_w;
+  lay->reserved = 0;
   int h = H, w = W;
   for (int l = 0; l < RCB_MAX_LEVELS; ++l) {
     if (l < levels) {
       if (h < 1 || w < 1) return RCB_ERR_INVALID_ARGUMENT;  // pooled away (reference would fail too)
       lay->H[l] = h;
       lay->W[l] = w;
-      lay->row_stride[l] = (w + align_elems - 1) / align_elems * align_elems;
-      lay->plane_stride[l] = (long long)h * lay->row_stride[l];
+      lay->tiles_x[l] = (w + tile_w - 1) / tile_w;
+      lay->tiles_y[l] = (h + 3) / 4;
+      lay->plane_stride[l] = (long long)lay->tiles_x[l] * lay->tiles_y[l] * 4 * tile_w;
       lay->level_bytes[l] = (long long)B * H * W * lay->plane_stride[l] * esize;
       h /= 2;
       w /= 2;
     } else {
-      lay->H[l] = lay->W[l] = lay->row_stride[l] = 0;
+      lay->H[l] = lay->W[l] = lay->tiles_x[l] = lay->tiles_y[l] = 0;
       lay->plane_stride[l] = lay->level_bytes[l] = 0;
     }
   }

@@ -34,7 +34,7 @@ def test_library_exports_every_declared_symbol(lib):
 
 
 def test_status_strings(lib):
-    assert lib.rcb_abi_version() == 1
+    assert lib.rcb_abi_version() == 2
     assert lib.rcb_status_string(0) == b"ok"
     assert b"invalid" in lib.rcb_status_string(-1)
     assert b"unsupported" in lib.rcb_status_string(-2)
@@ -46,12 +46,13 @@ def test_status_strings(lib):
 def test_pyramid_layout_floor_halving_and_padding(lib, H, W, want_h, want_w):
     lay = _cabi.pyramid_layout(3, H, W, 4)
     assert list(lay.H) == want_h and list(lay.W) == want_w  # core/corr.py:52-54 floor mode
+    assert lay.tile_w == 4
     for l in range(4):
-        assert lay.row_stride[l] >= lay.W[l] and lay.row_stride[l] % 4 == 0  # 16-byte rows
-        assert lay.plane_stride[l] == lay.H[l] * lay.row_stride[l]
+        assert lay.tiles_x[l] == -(-lay.W[l] // 4) and lay.tiles_y[l] == -(-lay.H[l] // 4)  # 4x4 tiles of 64 bytes
+        assert lay.plane_stride[l] == lay.tiles_x[l] * lay.tiles_y[l] * 16
         assert lay.level_bytes[l] == 3 * H * W * lay.plane_stride[l] * 4
     half = _cabi.pyramid_layout(3, H, W, 4, _cabi.F16)
-    assert all(half.row_stride[l] % 8 == 0 for l in range(4))
+    assert half.tile_w == 8 and all(half.tiles_x[l] == -(-half.W[l] // 8) for l in range(4))
 
 
 def test_layout_rejects_bad_arguments(lib):
