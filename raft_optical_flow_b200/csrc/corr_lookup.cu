@@ -6,18 +6,18 @@
 // (2r+1)^2 outputs the update block consumes.  HBM-bound gather: see DESIGN.md "K2".
 //
 // Work decomposition
-//   CTA   = 32 consecutive query pixels in flattened (h, w) order (so every output channel is written
-//           as one 128-byte line) of ONE level; 128 threads, ~21 KB of shared memory, so ~9 CTAs are
-//           resident per SM and their fetch / math / store phases overlap.
-//   fetch = all threads issue 16-byte cp.async (L2-only, zero-fill) for the aligned chunks that cover
-//           each window row; out-of-plane rows/chunks are zero-filled by the copy itself, which IS the
-//           zeros-padding of grid_sample.  Planes are stored as 4x4 tiles of 64 bytes (one DRAM atom), so
-//           a (2r+2)^2 window touches ~3.25^2 atoms instead of ~1.6 per row.
-//   math  = lane = query, the 4 warps split the output rows.  The window of a lane is read back with
-//           conflict-free LDS.128 (per-query block stride is an odd number of 16-byte units), aligned
-//           with two select stages, separable bilinear weights (all (2r+1)^2 samples of one level share
-//           the same fractional offset because the window offsets are integers).
-//   store = lane = query => 32 lanes write 32 consecutive floats of one output channel.
+//   CTA   = 32 consecutive query pixels in flattened (h, w) order of ONE level; 4 threads per query; a
+//           warp owns 8 queries end to end, so there is no block-level barrier.  ~21 KB of shared memory.
+//   fetch = 16-byte cp.async (L2-only, zero-fill): out-of-plane rows/chunks are zero-filled by the copy
+//           itself, which IS the zeros-padding of grid_sample.  Planes are stored as 4x4 tiles of 64 bytes
+//           (one DRAM atom), so a (2r+2)^2 window touches ~3.25^2 atoms instead of ~1.6 per row; the copy
+//           un-tiles into row-major window rows in shared memory.
+//   math  = the 4 lanes of a query split the (2r+1) x offsets; two LDS.128 per window row and lane, two
+//           select stages for the 4-byte phase, separable bilinear weights (all (2r+1)^2 samples of one
+//           level share the same fractional offset because the window offsets are integers).
+//   store = one instruction writes 4 channels x 8 consecutive queries (full 32-byte sectors).
+// The kernel is bound by the L1/shared-memory pipe, so the mappings above are chosen to
+// minimise cache lines per copy instruction and shared-memory wavefronts per output.
 #include "rcb_common.cuh"
 
 namespace rcb {
@@ -27,11 +27,25 @@ struct LookupCfg {
   static constexpr int RD = 2 * R + 1;
   static constexpr int ROWS = 2 * R + 2;           // taps per axis
   static constexpr int NCH = (ROWS + 3 + 3) / 4;   // 16-byte chunks covering ROWS floats at any 4-byte phase
-  static constexpr int BLK16 = ROWS * NCH + 1;     // 16-byte units per (level, query) block -- odd
+  // Shared-memory window of one query: ROWS rows of RS 16-byte units (RS odd), queries S units apart with
+  // S = 4 (mod 8).  With these strides both access patterns of a quarter warp (2 queries x 4 lanes) are free of
+  // bank conflicts: the fetch writes 4 consecutive rows of one chunk column per query (bank groups
+  // {0,RS,2RS,3RS} and the same +4), the math reads 1-3 neighbouring chunks of one row per query.
+  static constexpr int RS = NCH | 1;
+  static constexpr int BLK16 = (ROWS * RS + 3) / 8 * 8 + 4;
   static constexpr int QT = 32;                    // queries per CTA
   static constexpr int THREADS = 128;
-  static_assert((BLK16 & 1) == 1, "block stride must be odd for conflict-free LDS.128");
+  static_assert(BLK16 >= ROWS * RS && (BLK16 & 7) == 4, "query stride must be 4 mod 8 sixteen-byte units");
 };
+
+// streaming 16-byte load: read-only path, do not allocate in L1
+RCB_DEVINL float4 ld_nc_f4(const float* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p));
+  return v;
+}
 
 struct LevelCoord {
   int xs, ys;    // integer position of tap (0,0)
@@ -59,11 +73,10 @@ template <int R>
 __global__ void __launch_bounds__(LookupCfg<R>::THREADS)
 lookup_f32_kernel(PyramidDev pyr, const float* __restrict__ coords, float* __restrict__ out, int Q, int L) {
   using Cfg = LookupCfg<R>;
-  constexpr int RD = Cfg::RD, ROWS = Cfg::ROWS, NCH = Cfg::NCH, BLK16 = Cfg::BLK16, QT = Cfg::QT;
-  __shared__ float4 win[QT * BLK16];  // one level of 32 query windows, 16-byte chunks
-  __shared__ float s_cx[QT], s_cy[QT];
+  constexpr int RD = Cfg::RD, ROWS = Cfg::ROWS, NCH = Cfg::NCH, RS = Cfg::RS, BLK16 = Cfg::BLK16, QT = Cfg::QT;
+  __shared__ float4 win[QT * BLK16];  // one level of 32 query windows, row-major rows of RS 16-byte units
 
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31;
   const int l = blockIdx.y;
   const int b = blockIdx.z;
   const int q0 = blockIdx.x * QT;
@@ -71,81 +84,117 @@ lookup_f32_kernel(PyramidDev pyr, const float* __restrict__ coords, float* __res
   const long long ps = pyr.plane_stride[l];
   const float* __restrict__ base = static_cast<const float*>(pyr.ptr[l]);
 
-  if (tid < QT) {
-    const int q = q0 + tid;
-    float cx = -1.0e6f, cy = -1.0e6f;  // lanes past the end of the image fetch nothing
-    if (q < Q) {
-      cx = __ldg(coords + (long long)(b * 2 + 0) * Q + q);
-      cy = __ldg(coords + (long long)(b * 2 + 1) * Q + q);
-    }
-    s_cx[tid] = cx;
-    s_cy[tid] = cy;
+  // Thread t serves query q0 + t/4 in BOTH phases, so a warp only ever touches the windows of its own
+  // 8 queries: no block-level barrier, the 4 warps of the CTA run independently.
+  const int ql = tid >> 2;   // query within the CTA
+  const int sub = tid & 3;   // fetch: row inside a 4x4 tile; math: group of x offsets
+  const int q = q0 + ql;
+  const bool q_ok = q < Q;
+  float cx = -1.0e6f, cy = -1.0e6f;  // queries past the end fetch nothing and store nothing
+  if (q_ok) {
+    cx = __ldg(coords + (long long)(b * 2 + 0) * Q + q);
+    cy = __ldg(coords + (long long)(b * 2 + 1) * Q + q);
   }
-  __syncthreads();
-
-  // ---- fetch: zero-filling 16-byte async copies of every window row ------------------------
-  // 4 consecutive lanes cover the (up to) 64-byte span of one window row; chunks the window does not reach
-  // are not fetched at all.
-  const long long q_base = (long long)b * Q + q0;
-  const uint32_t dst0 = smem_u32(win);
-  for (int i = tid; i < QT * ROWS * NCH; i += Cfg::THREADS) {
-    const int c = i % NCH;
-    const int t = i / NCH;
-    const int j = t % ROWS;
-    const int q = t / ROWS;
-    const LevelCoord lc = level_coord<R>(s_cx[q], s_cy[q], l, Hl, Wl);
-    const int ph = lc.xs & 3;
-    if (4 * c >= ph + ROWS) continue;   // chunk lies beyond the last tap of this row
-    const int xa = lc.xs - ph;          // 16-byte aligned start (may be negative)
-    const int y = lc.ys + j;
-    const int xc = xa + 4 * c;
-    const bool ok = (y >= 0) && (y < Hl) && (xc >= 0) && (xc < Wl);
-    const int nvalid = min(4, Wl - xc);
-    // an aligned 4-float chunk of a row is exactly one 16-byte row of one 4x4 tile
-    const float* src = ok ? base + (q_base + q) * ps + tile_off(y, xc, tw) : base;
-    cp_async16_zfill(dst0 + (uint32_t)((q * BLK16 + j * NCH + c) * 16), src, ok ? nvalid * 4 : 0);
-  }
-  cp_async_commit();
-  cp_async_wait<0>();
-  __syncthreads();
-
-  // ---- math + store: lane = query, the 4 warps split the (2r+1) output rows ------------------
-  const int lane = tid & 31, warp = tid >> 5;
-  constexpr int NW = Cfg::THREADS / 32;
-  const int b_begin = (RD * warp) / NW, b_end = (RD * (warp + 1)) / NW;  // output rows (y offsets) of this warp
-  if (b_begin == b_end) return;
-  const bool q_ok = q0 + lane < Q;
-  const LevelCoord lc = level_coord<R>(s_cx[lane], s_cy[lane], l, Hl, Wl);
+  const LevelCoord lc = level_coord<R>(cx, cy, l, Hl, Wl);
   const int ph = lc.xs & 3;
-  const float fx = lc.fx, fy = lc.fy, gx = 1.0f - lc.fx, gy = 1.0f - lc.fy;
-  const float4* blk = win + lane * BLK16;
-  float* o = out + ((long long)b * L + l) * RD * RD * Q + q0 + lane;
-  float prev[RD];
-  for (int j = b_begin; j <= b_end; ++j) {  // input rows b_begin .. b_end
-    float wv[4 * NCH];
+  float4* blk = win + ql * BLK16;
+
+  // ---- fetch: 16-byte loads through registers, un-tiling on the fly --------------------------------
+  // Lane (query, r) loads row r of every 4x4 tile the window overlaps: the 4 lanes of a query cover one
+  // whole 64-byte tile per instruction, which the L1 tag stage turns into ONE two-sector request (cp.async.cg
+  // would issue one request per lane: the kernel is bound by the L1->L2 request port).
+  // All loads of a thread are issued before the first use.  Rows/chunks outside the plane stay zero, which
+  // IS the zeros padding of grid_sample; tile rows outside the window and chunks the window does not reach
+  // are not fetched at all.
+  if (q_ok) {
+    const int xa = lc.xs - ph;         // first chunk column (multiple of 4, may be negative)
+    const int ty0 = lc.ys >> 2;        // first tile row (arithmetic shift: floor)
+    const int nchunk = (ph + ROWS + 3) >> 2;
+    const float* plane = base + ((long long)b * Q + q) * ps;
+    int coff[NCH], cvalid[NCH];        // per chunk column: offset of its tile inside a tile row, valid floats
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
-      const float4 v = blk[j * NCH + c];
-      wv[4 * c + 0] = v.x;
-      wv[4 * c + 1] = v.y;
-      wv[4 * c + 2] = v.z;
-      wv[4 * c + 3] = v.w;
+      const int xc = xa + 4 * c;
+      const bool ok = (c < nchunk) && (xc >= 0) && (xc < Wl);
+      coff[c] = ok ? (xc >> 2) << 4 : 0;
+      cvalid[c] = ok ? min(4, Wl - xc) : (c < nchunk ? 0 : -1);  // -1: the window does not reach this chunk
     }
-    float v1[ROWS + 2];
+    constexpr int NTI = (ROWS + 3 + 3) / 4;  // tile rows a window can overlap
+    float4 v[NTI][NCH];
+    int jrow[NTI];
 #pragma unroll
-    for (int i = 0; i < ROWS + 2; ++i) v1[i] = (ph & 1) ? wv[i + 1] : wv[i];
-    float s[ROWS];
+    for (int ti = 0; ti < NTI; ++ti) {
+      const int y = ((ty0 + ti) << 2) + sub;
+      const int j = y - lc.ys;
+      jrow[ti] = (j >= 0 && j < ROWS) ? j : -1;
+      const bool y_ok = (jrow[ti] >= 0) && (y >= 0) && (y < Hl);
+      const float* trow = plane + (((long long)(y >> 2) * tw) << 4) + ((y & 3) << 2);
 #pragma unroll
-    for (int i = 0; i < ROWS; ++i) s[i] = (ph & 2) ? v1[i + 2] : v1[i];
-    float t[RD];
+      for (int c = 0; c < NCH; ++c) {
+        v[ti][c] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (y_ok && cvalid[c] > 0) v[ti][c] = ld_nc_f4(trow + coff[c]);
+      }
+    }
+    if (Wl & 3) {  // the last chunk of a row may hang over the right edge: zero the overhang
 #pragma unroll
-    for (int a = 0; a < RD; ++a) t[a] = gx * s[a] + fx * s[a + 1];
-    if (j > b_begin && q_ok) {
+      for (int c = 0; c < NCH; ++c) {
+        if (cvalid[c] > 0 && cvalid[c] < 4) {
 #pragma unroll
-      for (int a = 0; a < RD; ++a) o[(long long)(a * RD + (j - 1)) * Q] = gy * prev[a] + fy * t[a];
+          for (int ti = 0; ti < NTI; ++ti) {
+            if (cvalid[c] < 2) v[ti][c].y = 0.f;
+            if (cvalid[c] < 3) v[ti][c].z = 0.f;
+            v[ti][c].w = 0.f;
+          }
+        }
+      }
     }
 #pragma unroll
-    for (int a = 0; a < RD; ++a) prev[a] = t[a];
+    for (int ti = 0; ti < NTI; ++ti) {
+      if (jrow[ti] < 0) continue;
+#pragma unroll
+      for (int c = 0; c < NCH; ++c)
+        if (cvalid[c] >= 0) blk[jrow[ti] * RS + c] = v[ti][c];
+    }
+  }
+  __syncwarp();
+
+  // ---- math + store: lane = (query, group of x offsets) ------------------------------------------
+  // The (2r+1) x offsets are split over the 4 lanes of a query; a lane needs at most 4 consecutive taps of
+  // every window row = two 16-byte chunks (LDS.128 x2, the 4 lanes of a query mostly share addresses), aligns
+  // them with two select stages and applies the separable bilinear weights (all samples of one level share the
+  // same fractional offset).  A store instruction writes 4 channels x 8 consecutive queries (32-byte sectors).
+  if (!q_ok) return;
+  const int a0 = (RD * sub) >> 2, a1 = (RD * (sub + 1)) >> 2;  // x offsets [a0, a1)
+  const int na = a1 - a0;                                      // <= 3
+  const int start = ph + a0;
+  const int k0 = start >> 2, off = start & 3;
+  const int k1 = min(k0 + 1, NCH - 1);
+  const float fx = lc.fx, fy = lc.fy, gx = 1.0f - lc.fx, gy = 1.0f - lc.fy;
+  float* o = out + (((long long)b * L + l) * RD * RD + (long long)a0 * RD) * Q + q;
+  const long long sa = (long long)RD * Q;  // channel stride of one x offset
+  float prev[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int j = 0; j < ROWS; ++j) {
+    const float4 u0 = blk[j * RS + k0];
+    const float4 u1 = blk[j * RS + k1];
+    const float w[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+    float v1[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) v1[i] = (off & 1) ? w[i + 1] : w[i];
+    float sv[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) sv[i] = (off & 2) ? v1[i + 2] : v1[i];
+    float t[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) t[i] = gx * sv[i] + fx * sv[i + 1];
+    if (j > 0) {
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+        if (i < na) o[i * sa] = gy * prev[i] + fy * t[i];
+      o += Q;
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) prev[i] = t[i];
   }
 }
 

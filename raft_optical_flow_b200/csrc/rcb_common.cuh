@@ -78,9 +78,15 @@ inline int fill_layout(int B, int H, int W, int levels, int dtype, rcb_pyramid_l
 // ---- async copy (LDGSTS) with zero fill -------------------------------------------------
 RCB_DEVINL uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-// 16-byte global->shared copy through L2 only; bytes beyond src_bytes are written as zero.
+// 16-byte global->shared copy; bytes beyond src_bytes are written as zero.
+// .cg bypasses L1 (every lane's 16 bytes is its own L2 request); .ca goes through the L1 tag stage, which merges
+// the lanes of one instruction that hit the same 32-byte sector into one request.
 RCB_DEVINL void cp_async16_zfill(uint32_t dst_smem, const void* src, int src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst_smem), "l"(src), "r"(src_bytes)
+               : "memory");
+}
+RCB_DEVINL void cp_async16_ca_zfill(uint32_t dst_smem, const void* src, int src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst_smem), "l"(src), "r"(src_bytes)
                : "memory");
 }
 RCB_DEVINL void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
