@@ -40,13 +40,14 @@ constexpr int BN = PH * PW;      // 128 targets per tile (TMEM columns)
 constexpr int BK = 64;           // bf16 channels per smem stage row (128 bytes, SWIZZLE_128B)
 constexpr int UMMA_K = 16;
 constexpr int MAX_KB = 4;        // Kp <= 256
-constexpr int MAX_STAGE = 8;     // B ring depth is chosen at launch from the shared memory left over by A
-constexpr int NACC = 4;          // TMEM accumulator buffers (4 x 128 columns)
+constexpr int MAX_STAGE = 12;    // B ring depth is chosen at launch from the shared memory left over by A
+constexpr int MAX_ACC = 4;       // TMEM accumulator buffers (128 columns each); count chosen at launch
 constexpr int A_TILE_BYTES = BM * BK * 2;  // 16 KB
 constexpr int B_TILE_BYTES = BN * BK * 2;  // 16 KB
 constexpr int STG_BYTES = 4096;            // one staged store box per warp
 constexpr int NUM_EPI_WARPS = 4;
-constexpr int THREADS = 32 * (2 + NUM_EPI_WARPS);
+constexpr int THREADS = 32 * (2 + NUM_EPI_WARPS);      // A tiles in shared memory (SS MMA)
+constexpr int THREADS_TS = THREADS + 32 * 4;           // + 4 warps that place A in tensor memory (TS MMA)
 
 // Dynamic shared memory (all tile buffers 1024-byte aligned for the swizzle atoms):
 //   [0, a_bytes)            resident A tiles, index part * kblocks + kb
@@ -70,6 +71,10 @@ struct Params {
   float scale;      // 1 / sqrt(C)
   int direct_store; // debug: bypass the TMA stores
   int nstage, b_off, stg_off, bar_off;  // shared memory carve-up (bytes)
+  int nacc, acc_col0;                   // TMEM: accumulator count, first accumulator column
+  int Kp;                               // padded channel count
+  const uint32_t* a_pack;               // packed bf16 A operand, [part][B][Q][Kp/2] 32-bit words (TS kernel)
+  unsigned long long* prof;  // debug: per-CTA cycle counters (16 per CTA), null in production
   int debug_skip;   // debug bitmask: 1 skip L0 TMA store issue, 2 skip L1 store, 4 skip L2/L3, 8 skip staging writes
   float* pyr[RCB_MAX_LEVELS];
   int Hl[RCB_MAX_LEVELS], Wl[RCB_MAX_LEVELS], tx[RCB_MAX_LEVELS];  // level sizes, tiles per tile row
@@ -115,6 +120,13 @@ RCB_DEVINL bool elect_one() {
       "selp.u32 %0, 1, 0, P;\n\t}"
       : "=r"(pred));
   return pred != 0;
+}
+// mbar_wait that adds the cycles spent waiting to *acc (profiling builds of the launch only)
+RCB_DEVINL void mbar_wait_t(uint32_t bar, uint32_t parity, long long* acc) {
+  if (acc == nullptr) { mbar_wait(bar, parity); return; }
+  const long long t0 = clock64();
+  mbar_wait(bar, parity);
+  *acc += clock64() - t0;
 }
 RCB_DEVINL void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 RCB_DEVINL void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -162,6 +174,28 @@ RCB_DEVINL void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint3
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// same with the A operand in tensor memory (lane = row, one 32-bit column = two consecutive bf16 of K)
+RCB_DEVINL void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// registers -> tensor memory: lane i of the warp writes 32 consecutive 32-bit columns of TMEM lane (base + i)
+RCB_DEVINL void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+        "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+        "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+RCB_DEVINL void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // mbarrier arrives when all previously issued tcgen05.mma of this thread have completed
 RCB_DEVINL void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -251,7 +285,12 @@ RCB_DEVINL UnitCoord decode_unit(const Params& p, int u) {
   return c;
 }
 
-__global__ void __launch_bounds__(THREADS, 1)
+// TS = false: A tiles resident in shared memory (SS MMA), 192 threads.
+// TS = true : A resident in tensor memory (TS MMA), written there by 4 extra warps; the MMA then reads only B from
+//             shared memory, which halves its shared-memory traffic (the kernel is shared-memory-bandwidth bound:
+//             an M=128,N=128 SS MMA alone consumes the full 128 B/clk) and frees 128 KB for a deeper B ring.
+template <bool TS>
+__global__ void __launch_bounds__(TS ? THREADS_TS : THREADS, 1)
 build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                 const __grid_constant__ CUtensorMap map_l0, const __grid_constant__ CUtensorMap map_l1,
                 const Params p) {
@@ -266,13 +305,14 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   auto b_full = [&](int s) { return bar0 + 16 + 8 * s; };
   auto b_empty = [&](int s) { return bar0 + 16 + 8 * MAX_STAGE + 8 * s; };
   auto acc_full = [&](int s) { return bar0 + 16 + 16 * MAX_STAGE + 8 * s; };
-  auto acc_empty = [&](int s) { return bar0 + 16 + 16 * MAX_STAGE + 8 * NACC + 8 * s; };
-  const uint32_t tmem_slot = bar0 + 16 + 16 * MAX_STAGE + 16 * NACC;
+  auto acc_empty = [&](int s) { return bar0 + 16 + 16 * MAX_STAGE + 8 * MAX_ACC + 8 * s; };
+  const uint32_t tmem_slot = bar0 + 16 + 16 * MAX_STAGE + 16 * MAX_ACC;
+  const int NACC = p.nacc;
   volatile uint32_t* tmem_slot_ptr =
-      reinterpret_cast<volatile uint32_t*>(smem + p.bar_off + 16 + 16 * MAX_STAGE + 16 * NACC);
+      reinterpret_cast<volatile uint32_t*>(smem + p.bar_off + 16 + 16 * MAX_STAGE + 16 * MAX_ACC);
 
   if (threadIdx.x == 0) {
-    mbar_init(a_full, 1);
+    mbar_init(a_full, TS ? 4 : 1);  // TS: one arrival per A-loader warp; SS: the producer's expect_tx
     mbar_init(a_empty, 1);
     for (int s = 0; s < NSTAGE; ++s) {
       mbar_init(b_full(s), 1);
@@ -284,7 +324,7 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, NACC * BN);
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -295,22 +335,28 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     int s = 0;           // B ring slot
     uint32_t ph = 0;     // its phase
     uint32_t nunit = 0;
+    long long w_b = 0, w_a = 0;
+    long long* pw_b = p.prof ? &w_b : nullptr;
+    long long* pw_a = p.prof ? &w_a : nullptr;
+    const long long t_begin = clock64();
     for (int u = blockIdx.x; u < p.units; u += gridDim.x, ++nunit) {
       const UnitCoord uc = decode_unit(p, u);
-      if (nunit > 0) mbar_wait(a_empty, (nunit - 1) & 1);  // previous unit's MMAs have drained A
-      if (elect_one()) {
-        mbar_expect_tx(a_full, (uint32_t)(p.parts * p.kblocks * A_TILE_BYTES));
-        for (int part = 0; part < p.parts; ++part)
-          for (int kb = 0; kb < p.kblocks; ++kb)
-            tma_load_3d(smem_base + (part * p.kblocks + kb) * A_TILE_BYTES, &map_a, a_full, kb * BK, uc.mt * BM,
-                        part * p.B + uc.b);
+      if (!TS) {
+        if (nunit > 0) mbar_wait_t(a_empty, (nunit - 1) & 1, pw_a);  // previous unit's MMAs have drained A
+        if (elect_one()) {
+          mbar_expect_tx(a_full, (uint32_t)(p.parts * p.kblocks * A_TILE_BYTES));
+          for (int part = 0; part < p.parts; ++part)
+            for (int kb = 0; kb < p.kblocks; ++kb)
+              tma_load_3d(smem_base + (part * p.kblocks + kb) * A_TILE_BYTES, &map_a, a_full, kb * BK, uc.mt * BM,
+                          part * p.B + uc.b);
+        }
+        __syncwarp();
       }
-      __syncwarp();
       for (int pi = uc.p_begin; pi < uc.p_end; ++pi) {
         const int py = pi / p.pcols, px = pi % p.pcols;
         for (int kb = 0; kb < p.kblocks; ++kb)
           for (int part = 0; part < p.parts; ++part) {
-            mbar_wait(b_empty(s), ph ^ 1);
+            mbar_wait_t(b_empty(s), ph ^ 1, pw_b);
             if (elect_one()) {
               if (p.debug_skip & 16) {
                 mbar_arrive(b_full(s));
@@ -325,39 +371,54 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           }
       }
     }
+    if (p.prof && lane == 0) {
+      p.prof[blockIdx.x * 16 + 0] = clock64() - t_begin;
+      p.prof[blockIdx.x * 16 + 1] = w_b;
+      p.prof[blockIdx.x * 16 + 2] = w_a;
+    }
   } else if (warp == 1) {
     // =============================== MMA issuer (whole warp runs the loop, one elected lane issues) ======
     constexpr uint32_t idesc = make_idesc();
     const uint64_t desc_base = make_smem_desc(0);  // everything but the start address
-    int s = 0;
-    uint32_t ph = 0, tile = 0, nunit = 0;
+    int s = 0, buf = 0;
+    uint32_t ph = 0, aph = 0, tile = 0, nunit = 0;
+    long long w_bf = 0, w_acc = 0, w_af = 0;
+    long long* pw_bf = p.prof ? &w_bf : nullptr;
+    long long* pw_acc = p.prof ? &w_acc : nullptr;
+    long long* pw_af = p.prof ? &w_af : nullptr;
+    const long long t_begin = clock64();
     for (int u = blockIdx.x; u < p.units; u += gridDim.x, ++nunit) {
       const UnitCoord uc = decode_unit(p, u);
-      mbar_wait(a_full, nunit & 1);
+      mbar_wait_t(a_full, nunit & 1, pw_af);
       tc_fence_after();
       for (int pi = uc.p_begin; pi < uc.p_end; ++pi, ++tile) {
-        const int buf = tile % NACC;
-        mbar_wait(acc_empty(buf), ((tile / NACC) & 1) ^ 1);
+        mbar_wait_t(acc_empty(buf), aph ^ 1, pw_acc);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + buf * BN;
+        const uint32_t d_tmem = tmem_base + p.acc_col0 + buf * BN;
         uint32_t acc = 0;
         for (int kb = 0; kb < p.kblocks; ++kb) {
+          const uint32_t ta_hi = tmem_base + kb * (BK / 2);                 // TS: A columns of this k-block
+          const uint32_t ta_lo = tmem_base + (p.Kp >> 1) + kb * (BK / 2);
           const uint64_t a_hi = desc_base | (uint64_t)(((smem_base + kb * A_TILE_BYTES) >> 4) & 0x3FFF);
           const uint64_t a_lo = desc_base | (uint64_t)(((smem_base + (p.kblocks + kb) * A_TILE_BYTES) >> 4) & 0x3FFF);
           for (int part = 0; part < p.parts; ++part) {
-            mbar_wait(b_full(s), ph);
+            mbar_wait_t(b_full(s), ph, pw_bf);
             tc_fence_after();
             const uint64_t bdesc = desc_base | (uint64_t)(((smem_base + p.b_off + s * B_TILE_BYTES) >> 4) & 0x3FFF);
             if (elect_one()) {
               if (!(p.debug_skip & 32)) {
 #pragma unroll
-                for (int k = 0; k < BK / UMMA_K; ++k) {  // +32 bytes per K step inside the swizzled row
-                  umma_bf16(d_tmem, a_hi + 2 * k, bdesc + 2 * k, idesc, acc);
+                for (int k = 0; k < BK / UMMA_K; ++k) {  // +32 bytes (smem) / +8 columns (TMEM) per K step
+                  if (TS) umma_bf16_ts(d_tmem, ta_hi + 8 * k, bdesc + 2 * k, idesc, acc);
+                  else umma_bf16(d_tmem, a_hi + 2 * k, bdesc + 2 * k, idesc, acc);
                   acc = 1;
                 }
                 if (part == 0 && p.parts > 1) {  // B_hi also meets A_lo
 #pragma unroll
-                  for (int k = 0; k < BK / UMMA_K; ++k) umma_bf16(d_tmem, a_lo + 2 * k, bdesc + 2 * k, idesc, 1u);
+                  for (int k = 0; k < BK / UMMA_K; ++k) {
+                    if (TS) umma_bf16_ts(d_tmem, ta_lo + 8 * k, bdesc + 2 * k, idesc, 1u);
+                    else umma_bf16(d_tmem, a_lo + 2 * k, bdesc + 2 * k, idesc, 1u);
+                  }
                 }
               }
               if (p.debug_skip & 128) mbar_arrive(b_empty(s));
@@ -373,17 +434,29 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           else umma_commit(acc_full(buf));
         }
         __syncwarp();
+        if (++buf == NACC) { buf = 0; aph ^= 1; }
       }
       if (elect_one()) umma_commit(a_empty);
       __syncwarp();
     }
-  } else {
+    if (p.prof && lane == 0) {
+      p.prof[blockIdx.x * 16 + 3] = clock64() - t_begin;
+      p.prof[blockIdx.x * 16 + 4] = w_bf;
+      p.prof[blockIdx.x * 16 + 5] = w_acc;
+      p.prof[blockIdx.x * 16 + 6] = w_af;
+    }
+  } else if (warp < 2 + NUM_EPI_WARPS) {
     // =============================== epilogue ===============================
     const int ew = warp - 2;             // staging slot
+    int buf = 0;
+    uint32_t aph = 0;
     const int lane_q = (warp & 3) * 32;  // TMEM lane quarter this warp may access
     unsigned char* stg = smem + p.stg_off + ew * 2 * STG_BYTES;
     uint32_t nstore = 0;  // staged stores issued by this warp (buffer = nstore & 1)
     uint32_t tile = 0;
+    long long w_full = 0, w_st = 0, w_ld = 0;
+    long long* pw_full = p.prof ? &w_full : nullptr;
+    const long long t_begin = clock64();
     for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
       const UnitCoord uc = decode_unit(p, u);
       const int q_w = uc.mt * BM + lane_q;  // first query of this warp
@@ -393,10 +466,9 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       for (int pi = uc.p_begin; pi < uc.p_end; ++pi, ++tile) {
         const int py = pi / p.pcols, px = pi % p.pcols;
         const int y0 = py * PH, x0 = px * PW;
-        const int buf = tile % NACC;
-        mbar_wait(acc_full(buf), (tile / NACC) & 1);
+        mbar_wait_t(acc_full(buf), aph, pw_full);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)lane_q << 16) + buf * BN;
+        const uint32_t taddr = tmem_base + ((uint32_t)lane_q << 16) + p.acc_col0 + buf * BN;
         float l1[4][8];
 #pragma unroll
         for (int band = 0; band < 2; ++band) {  // 4 patch rows = one row of 4x4 tiles
@@ -405,8 +477,10 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 #pragma unroll
             for (int i = 0; i < 32; ++i) va[i] = vb[i] = 0.f;
           } else {
+            const long long t0 = p.prof ? clock64() : 0;
             tmem_ld32(taddr + band * 64, va);
             tmem_ld32(taddr + band * 64 + 32, vb);
+            if (p.prof) w_ld += clock64() - t0;
           }
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
@@ -438,8 +512,12 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             for (int half = 0; half < 2; ++half) {
               if (x0 + 8 * half >= p.W) break;  // warp-uniform: these tiles do not exist
               unsigned char* sb = stg + (nstore & 1) * STG_BYTES;
-              if (lane == 0) tma_store_wait_read<1>();  // the store that used this buffer has been read out
-              __syncwarp();
+              {
+                const long long t0 = p.prof ? clock64() : 0;
+                if (lane == 0) tma_store_wait_read<1>();  // the store that used this buffer has been read out
+                __syncwarp();
+                if (p.prof) w_st += clock64() - t0;
+              }
               if (!(p.debug_skip & 8)) {
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {  // chunk c = tile (c >> 2) of this half, tile row (c & 3)
@@ -465,6 +543,9 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(acc_empty(buf));
+        const int buf_done = buf;
+        (void)buf_done;
+        if (++buf == NACC) { buf = 0; aph ^= 1; }
 
         if (p.levels > 1) {
           const int y1 = y0 >> 1, x1 = x0 >> 1;  // 4 rows x 8 cols = 2 tiles = 128 contiguous bytes per query
@@ -520,14 +601,58 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         }
       }
     }
+    if (p.prof && lane == 0 && ew == 2) {  // warp 4 = TMEM lanes 0-31
+      p.prof[blockIdx.x * 16 + 7] = clock64() - t_begin;
+      p.prof[blockIdx.x * 16 + 8] = w_full;
+      p.prof[blockIdx.x * 16 + 9] = w_st;
+      p.prof[blockIdx.x * 16 + 10] = w_ld;
+      p.prof[blockIdx.x * 16 + 11] = tile;
+    }
     if (lane == 0) tma_store_wait_all();
+  } else if (TS) {
+    // =============================== A loaders (TS kernel): global -> registers -> tensor memory =========
+    // Warp w may touch TMEM lanes 32*(w%4)..+31 = queries of the 128-query tile; lane i copies the packed bf16 row
+    // of its query (Kp/2 32-bit words per part) into columns [part*Kp/2, ...) of its TMEM lane.
+    const int lane_q = (warp & 3) * 32;
+    const int words = p.Kp >> 1;  // 32-bit words per row and part (multiple of 32)
+    uint32_t nunit = 0;
+    for (int u = blockIdx.x; u < p.units; u += gridDim.x, ++nunit) {
+      const UnitCoord uc = decode_unit(p, u);
+      const int q = uc.mt * BM + lane_q + lane;
+      const bool q_ok = q < p.Q;
+      for (int part = 0; part < p.parts; ++part) {
+        // all loads of a part are in flight before the first store (128 registers at Kp = 256); the loads of
+        // part 0 are issued before waiting for the previous unit to release A
+        const uint4* row = reinterpret_cast<const uint4*>(
+            p.a_pack + (((long long)part * p.B + uc.b) * p.Q + (q_ok ? q : 0)) * words);
+        uint32_t r[MAX_KB][32];
+#pragma unroll
+        for (int ch = 0; ch < MAX_KB; ++ch) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (q_ok && ch * 32 < words) v = __ldg(row + ch * 8 + i);
+            r[ch][4 * i + 0] = v.x; r[ch][4 * i + 1] = v.y; r[ch][4 * i + 2] = v.z; r[ch][4 * i + 3] = v.w;
+          }
+        }
+        if (part == 0 && nunit > 0) mbar_wait(a_empty, (nunit - 1) & 1);  // previous unit's MMAs are done with A
+        if (part == 0) tc_fence_after();
+#pragma unroll
+        for (int ch = 0; ch < MAX_KB; ++ch)
+          if (ch * 32 < words) tmem_st32(tmem_base + ((uint32_t)lane_q << 16) + part * words + ch * 32, r[ch]);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_full);
+    }
   }
 
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, NACC * BN);
+    tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -636,6 +761,8 @@ int launch_build_tc(const float* f1, const float* f2, void* const* pyr, const rc
   p.scale = 1.0f / sqrtf((float)C);
   const char* dbg = getenv("RCB_TC_DIRECT_STORE");
   p.direct_store = (dbg && dbg[0] == '1') ? 1 : 0;
+  const char* prof = getenv("RCB_TC_PROF_PTR");  // debug: device buffer of 16 x 148 uint64 supplied by tools/time_build.py
+  p.prof = prof ? reinterpret_cast<unsigned long long*>(strtoull(prof, nullptr, 0)) : nullptr;
   const char* skip = getenv("RCB_TC_DEBUG_SKIP");
   p.debug_skip = skip ? atoi(skip) : 0;
   for (int l = 0; l < RCB_MAX_LEVELS; ++l) {
@@ -643,7 +770,18 @@ int launch_build_tc(const float* f1, const float* f2, void* const* pyr, const rc
     p.Hl[l] = lay.H[l]; p.Wl[l] = lay.W[l]; p.tx[l] = lay.tiles_x[l]; p.ps[l] = lay.plane_stride[l];
   }
 
-  const int a_bytes = parts * p.kblocks * A_TILE_BYTES;
+  const char* ss = getenv("RCB_TC_SS");  // debug: keep A in shared memory (SS MMA) instead of tensor memory
+  const bool ts = !(ss && ss[0] == '1');
+  p.Kp = Kp;
+  p.a_pack = reinterpret_cast<const uint32_t*>(a_pack);
+  if (ts) {
+    p.acc_col0 = (parts * (Kp / 2) + 127) / 128 * 128;  // A occupies the first parts*Kp/2 TMEM columns
+    p.nacc = (512 - p.acc_col0) / BN < MAX_ACC ? (512 - p.acc_col0) / BN : MAX_ACC;
+  } else {
+    p.acc_col0 = 0;
+    p.nacc = MAX_ACC;
+  }
+  const int a_bytes = ts ? 0 : parts * p.kblocks * A_TILE_BYTES;
   int nstage = (SMEM_BUDGET - BAR_BYTES - STG_TOTAL - a_bytes) / B_TILE_BYTES;
   if (nstage > MAX_STAGE) nstage = MAX_STAGE;
   if (const char* ns = getenv("RCB_TC_NSTAGE")) nstage = atoi(ns) < nstage ? atoi(ns) : nstage;
@@ -654,10 +792,16 @@ int launch_build_tc(const float* f1, const float* f2, void* const* pyr, const rc
   p.bar_off = p.stg_off + STG_TOTAL;
   const int smem_total = p.bar_off + BAR_BYTES;
 
-  cudaError_t e = cudaFuncSetAttribute(build_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET);
-  if (e != cudaSuccess) return (int)e;
   const int grid = p.units < kNumSMs ? p.units : kNumSMs;
-  build_tc_kernel<<<grid, THREADS, smem_total, s>>>(map_a, map_b, map_l0, map_l1, p);
+  if (ts) {
+    cudaError_t e = cudaFuncSetAttribute(build_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET);
+    if (e != cudaSuccess) return (int)e;
+    build_tc_kernel<true><<<grid, THREADS_TS, smem_total, s>>>(map_a, map_b, map_l0, map_l1, p);
+  } else {
+    cudaError_t e = cudaFuncSetAttribute(build_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET);
+    if (e != cudaSuccess) return (int)e;
+    build_tc_kernel<false><<<grid, THREADS, smem_total, s>>>(map_a, map_b, map_l0, map_l1, p);
+  }
   return launch_status();
 }
 
