@@ -43,7 +43,9 @@ constexpr int MAX_KB = 4;        // Kp <= 256
 constexpr int MAX_STAGE = 12;    // B ring depth is chosen at launch from the shared memory left over by A
 constexpr int MAX_ACC = 4;       // TMEM accumulator buffers (128 columns each); count chosen at launch
 constexpr int A_TILE_BYTES = BM * BK * 2;  // 16 KB
-constexpr int B_TILE_BYTES = BN * BK * 2;  // 16 KB
+constexpr int B_TILE_BYTES = BN * BK * 2;  // 16 KB: one TMA box (128 targets x 64 channels)
+constexpr int BOXES_PER_STAGE = 2;         // a ring stage = 2 boxes on one mbarrier: (kb,hi)+(kb,lo) or (kb)+(kb+1)
+constexpr int STAGE_BYTES = BOXES_PER_STAGE * B_TILE_BYTES;
 constexpr int STG_BYTES = 4096;            // one staged store box per warp
 constexpr int NUM_EPI_WARPS = 4;
 constexpr int THREADS = 32 * (2 + NUM_EPI_WARPS);      // A tiles in shared memory (SS MMA)
@@ -354,21 +356,26 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       }
       for (int pi = uc.p_begin; pi < uc.p_end; ++pi) {
         const int py = pi / p.pcols, px = pi % p.pcols;
-        for (int kb = 0; kb < p.kblocks; ++kb)
-          for (int part = 0; part < p.parts; ++part) {
-            mbar_wait_t(b_empty(s), ph ^ 1, pw_b);
-            if (elect_one()) {
-              if (p.debug_skip & 16) {
-                mbar_arrive(b_full(s));
-              } else {
-                mbar_expect_tx(b_full(s), B_TILE_BYTES);
-                tma_load_4d(smem_base + p.b_off + s * B_TILE_BYTES, &map_b, b_full(s), kb * BK, px * PW, py * PH,
-                            part * p.B + uc.b);
+        const int nb = p.kblocks * p.parts;  // boxes of this tile in (kb, part) order
+        for (int j = 0; j < nb; j += BOXES_PER_STAGE) {
+          mbar_wait_t(b_empty(s), ph ^ 1, pw_b);
+          if (elect_one()) {
+            const int nbox = min(BOXES_PER_STAGE, nb - j);
+            if (p.debug_skip & 16) {
+              mbar_arrive(b_full(s));
+            } else {
+              mbar_expect_tx(b_full(s), (uint32_t)(nbox * B_TILE_BYTES));
+              for (int t = 0; t < nbox; ++t) {
+                const int jj = j + t;
+                const int kb = p.parts == 2 ? jj >> 1 : jj, part = p.parts == 2 ? jj & 1 : 0;
+                tma_load_4d(smem_base + p.b_off + s * STAGE_BYTES + t * B_TILE_BYTES, &map_b, b_full(s), kb * BK, px * PW,
+                            py * PH, part * p.B + uc.b);
               }
             }
-            __syncwarp();
-            if (++s == NSTAGE) { s = 0; ph ^= 1; }
           }
+          __syncwarp();
+          if (++s == NSTAGE) { s = 0; ph ^= 1; }
+        }
       }
     }
     if (p.prof && lane == 0) {
@@ -396,17 +403,22 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + p.acc_col0 + buf * BN;
         uint32_t acc = 0;
-        for (int kb = 0; kb < p.kblocks; ++kb) {
-          const uint32_t ta_hi = tmem_base + kb * (BK / 2);                 // TS: A columns of this k-block
-          const uint32_t ta_lo = tmem_base + (p.Kp >> 1) + kb * (BK / 2);
-          const uint64_t a_hi = desc_base | (uint64_t)(((smem_base + kb * A_TILE_BYTES) >> 4) & 0x3FFF);
-          const uint64_t a_lo = desc_base | (uint64_t)(((smem_base + (p.kblocks + kb) * A_TILE_BYTES) >> 4) & 0x3FFF);
-          for (int part = 0; part < p.parts; ++part) {
-            mbar_wait_t(b_full(s), ph, pw_bf);
-            tc_fence_after();
-            const uint64_t bdesc = desc_base | (uint64_t)(((smem_base + p.b_off + s * B_TILE_BYTES) >> 4) & 0x3FFF);
-            if (elect_one()) {
-              if (!(p.debug_skip & 32)) {
+        const int nb = p.kblocks * p.parts;
+        for (int j = 0; j < nb; j += BOXES_PER_STAGE) {
+          mbar_wait_t(b_full(s), ph, pw_bf);
+          tc_fence_after();
+          if (elect_one()) {
+            const int nbox = min(BOXES_PER_STAGE, nb - j);
+            if (!(p.debug_skip & 32)) {
+              for (int t = 0; t < nbox; ++t) {
+                const int jj = j + t;
+                const int kb = p.parts == 2 ? jj >> 1 : jj, part = p.parts == 2 ? jj & 1 : 0;
+                const uint64_t bdesc =
+                    desc_base | (uint64_t)(((smem_base + p.b_off + s * STAGE_BYTES + t * B_TILE_BYTES) >> 4) & 0x3FFF);
+                const uint32_t ta_hi = tmem_base + kb * (BK / 2);  // TS: A columns of this k-block
+                const uint32_t ta_lo = tmem_base + (p.Kp >> 1) + kb * (BK / 2);
+                const uint64_t a_hi = desc_base | (uint64_t)(((smem_base + kb * A_TILE_BYTES) >> 4) & 0x3FFF);
+                const uint64_t a_lo = desc_base | (uint64_t)(((smem_base + (p.kblocks + kb) * A_TILE_BYTES) >> 4) & 0x3FFF);
 #pragma unroll
                 for (int k = 0; k < BK / UMMA_K; ++k) {  // +32 bytes (smem) / +8 columns (TMEM) per K step
                   if (TS) umma_bf16_ts(d_tmem, ta_hi + 8 * k, bdesc + 2 * k, idesc, acc);
@@ -421,13 +433,13 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                   }
                 }
               }
-              if (p.debug_skip & 128) mbar_arrive(b_empty(s));
-              else umma_commit(b_empty(s));  // frees the B stage once these MMAs have read it
             }
-            acc = 1;
-            __syncwarp();
-            if (++s == NSTAGE) { s = 0; ph ^= 1; }
+            if (p.debug_skip & 128) mbar_arrive(b_empty(s));
+            else umma_commit(b_empty(s));  // frees the stage once these MMAs have read it
           }
+          acc = 1;
+          __syncwarp();
+          if (++s == NSTAGE) { s = 0; ph ^= 1; }
         }
         if (elect_one()) {
           if (p.debug_skip & 256) mbar_arrive(acc_full(buf));
@@ -782,13 +794,13 @@ int launch_build_tc(const float* f1, const float* f2, void* const* pyr, const rc
     p.nacc = MAX_ACC;
   }
   const int a_bytes = ts ? 0 : parts * p.kblocks * A_TILE_BYTES;
-  int nstage = (SMEM_BUDGET - BAR_BYTES - STG_TOTAL - a_bytes) / B_TILE_BYTES;
+  int nstage = (SMEM_BUDGET - BAR_BYTES - STG_TOTAL - a_bytes) / STAGE_BYTES;
   if (nstage > MAX_STAGE) nstage = MAX_STAGE;
   if (const char* ns = getenv("RCB_TC_NSTAGE")) nstage = atoi(ns) < nstage ? atoi(ns) : nstage;
   if (nstage < 2) return RCB_ERR_UNSUPPORTED;
   p.nstage = nstage;
   p.b_off = a_bytes;
-  p.stg_off = p.b_off + nstage * B_TILE_BYTES;
+  p.stg_off = p.b_off + nstage * STAGE_BYTES;
   p.bar_off = p.stg_off + STG_TOTAL;
   const int smem_total = p.bar_off + BAR_BYTES;
 
