@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define RCB_ABI_VERSION 2
+#define RCB_ABI_VERSION 3
 #define RCB_MAX_LEVELS 4 /* core/raft.py:46-53 fixes corr_levels = 4 */
 #define RCB_MAX_RADIUS 4 /* core/raft.py:47,53: radius 3 (small) / 4 (full) */
 
@@ -105,6 +105,16 @@ RCB_API int rcb_corr_build(const float* fmap1, const float* fmap2, void* const* 
  *            (x/2^l + a - r, y/2^l + b - r)  -- the x offset is the slow index (core/corr.py:77-84). */
 RCB_API int rcb_corr_lookup(const void* const* pyr, const float* coords, float* out, int B, int H, int W,
                     int levels, int radius, int pyr_dtype, rcb_stream_t stream);
+
+/* Planned form: the lookup gathers every window with one TMA box, which needs tensor maps of the pyramid
+ * levels.  rcb_corr_lookup encodes them on every call; a caller that looks the same pyramid up many times
+ * (core/raft.py:214-219, once per GRU iteration) encodes them once into a host-side plan instead.
+ *   plan : HOST memory owned by the caller, >= rcb_corr_lookup_plan_bytes() bytes, 64-byte aligned; plain data,
+ *          may be copied/freed at will; valid while `pyr` buffers and geometry are unchanged. */
+RCB_API size_t rcb_corr_lookup_plan_bytes(void);
+RCB_API int rcb_corr_lookup_plan_init(void* plan, size_t plan_bytes, const void* const* pyr, int B, int H, int W,
+                              int levels, int radius, int pyr_dtype);
+RCB_API int rcb_corr_lookup_planned(const void* plan, const float* coords, float* out, rcb_stream_t stream);
 
 /* ---- K4: backward of the all-pairs path ---------------------------------------------------
  * Replaces what autograd records through core/corr.py:25-127 for train.py:212.

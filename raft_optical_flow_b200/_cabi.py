@@ -9,7 +9,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libraftcorr_b200.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 MAX_LEVELS = 4
 MAX_RADIUS = 4
 
@@ -45,6 +45,9 @@ SIGNATURES = {
     "rcb_corr_build_workspace_bytes": (ctypes.c_size_t, [_i, _i, _i, _i, _i]),
     "rcb_corr_build": (_i, [_vp, _vp, ctypes.POINTER(_vp), _i, _i, _i, _i, _i, _i, _i, _vp, ctypes.c_size_t, _vp]),
     "rcb_corr_lookup": (_i, [ctypes.POINTER(_vp), _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "rcb_corr_lookup_plan_bytes": (ctypes.c_size_t, []),
+    "rcb_corr_lookup_plan_init": (_i, [_vp, ctypes.c_size_t, ctypes.POINTER(_vp), _i, _i, _i, _i, _i, _i]),
+    "rcb_corr_lookup_planned": (_i, [_vp, _vp, _vp, _vp]),
     "rcb_corr_lookup_backward": (_i, [ctypes.POINTER(_vp), _vp, _vp, ctypes.POINTER(_vp), _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "rcb_corr_pool_backward": (_i, [ctypes.POINTER(_vp), _i, _i, _i, _i, _vp]),
     "rcb_corr_contract_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
@@ -90,3 +93,15 @@ def pyramid_layout(B, H, W, levels, dtype=F32):
     lay = PyramidLayout()
     check(lib().rcb_pyramid_layout_query(B, H, W, levels, dtype, ctypes.byref(lay)), "rcb_pyramid_layout_query")
     return lay
+
+
+class LookupPlan:
+    """Host-side lookup plan (rcb_corr_lookup_plan_*): the TMA tensor maps of one pyramid, encoded once."""
+
+    def __init__(self, ptrs, B, H, W, levels, radius, dtype=F32):
+        n = lib().rcb_corr_lookup_plan_bytes()
+        self._raw = ctypes.create_string_buffer(n + 64)
+        self.ptr = (ctypes.addressof(self._raw) + 63) & ~63
+        self.nbytes = n
+        check(lib().rcb_corr_lookup_plan_init(self.ptr, n, ptrs, B, H, W, levels, radius, dtype),
+              "rcb_corr_lookup_plan_init")

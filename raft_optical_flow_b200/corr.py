@@ -144,6 +144,8 @@ class _State:
         self.pyr = _Pyramid(B, H, W, levels, f1.device, pyr_dtype)
         self.dpyr = None
         _build(f1, f2, levels, mode, self.pyr)
+        with torch.cuda.device(f1.device):
+            self.plan = _cabi.LookupPlan(self.pyr.ptrs, B, H, W, levels, radius, pyr_dtype)
 
     def lookup(self, coords):
         B, two, H, W = coords.shape
@@ -152,9 +154,8 @@ class _State:
         rd = 2 * self.radius + 1
         out = torch.empty((B, self.levels * rd * rd, H, W), dtype=torch.float32, device=coords.device)
         with torch.cuda.device(coords.device):
-            _cabi.check(_cabi.lib().rcb_corr_lookup(self.pyr.ptrs, coords.data_ptr(), out.data_ptr(), B, H, W,
-                                                    self.levels, self.radius, self.pyr.dtype, _stream(coords)),
-                        "rcb_corr_lookup")
+            _cabi.check(_cabi.lib().rcb_corr_lookup_planned(self.plan.ptr, coords.data_ptr(), out.data_ptr(),
+                                                            _stream(coords)), "rcb_corr_lookup_planned")
         return out
 
 

@@ -64,6 +64,25 @@ int rcb_corr_lookup(const void* const* pyr, const float* coords, float* out, int
   return launch_lookup(pyr, lay, coords, out, B, H, W, radius, reinterpret_cast<cudaStream_t>(stream));
 }
 
+size_t rcb_corr_lookup_plan_bytes(void) { return lookup_plan_bytes(); }
+
+int rcb_corr_lookup_plan_init(void* plan, size_t plan_bytes, const void* const* pyr, int B, int H, int W,
+                              int levels, int radius, int pyr_dtype) {
+  if (!plan || !pyr) return RCB_ERR_INVALID_ARGUMENT;
+  if (!radius_ok(radius)) return RCB_ERR_UNSUPPORTED;
+  rcb_pyramid_layout lay;
+  int st = fill_layout(B, H, W, levels, pyr_dtype, &lay);
+  if (st != RCB_OK) return st;
+  for (int l = 0; l < levels; ++l)
+    if (!pyr[l] || !aligned16(pyr[l])) return RCB_ERR_INVALID_ARGUMENT;
+  return lookup_plan_init(plan, plan_bytes, pyr, lay, B, H, W, radius);
+}
+
+int rcb_corr_lookup_planned(const void* plan, const float* coords, float* out, rcb_stream_t stream) {
+  if (!plan || !coords || !out) return RCB_ERR_INVALID_ARGUMENT;
+  return launch_lookup_planned(plan, coords, out, reinterpret_cast<cudaStream_t>(stream));
+}
+
 int rcb_corr_lookup_backward(const void* const* pyr, const float* coords, const float* grad_out,
                              float* const* dpyr, float* dcoords, int B, int H, int W, int levels, int radius,
                              int pyr_dtype, rcb_stream_t stream) {

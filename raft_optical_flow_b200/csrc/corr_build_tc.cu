@@ -24,11 +24,10 @@
 //                 a level-k cell computed from a dropped row/col is itself outside H_k x W_k, i.e. tile
 //                 padding or a clipped tile.  Level 1 is TMA-stored, levels 2/3 (6% / 1.5% of the bytes)
 //                 are written with 32/8-byte global stores.
-#include <cudaTypedefs.h>
-
 #include <cstdlib>
 
 #include "rcb_common.cuh"
+#include "tma_util.cuh"
 
 namespace rcb {
 
@@ -82,82 +81,6 @@ struct Params {
   int Hl[RCB_MAX_LEVELS], Wl[RCB_MAX_LEVELS], tx[RCB_MAX_LEVELS];  // level sizes, tiles per tile row
   long long ps[RCB_MAX_LEVELS];
 };
-
-// ---- PTX wrappers ------------------------------------------------------------------------
-RCB_DEVINL void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-RCB_DEVINL void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-RCB_DEVINL void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-RCB_DEVINL bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// Bounded wait: a protocol bug traps (the launch fails with an error) instead of hanging the GPU.
-RCB_DEVINL void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 8000000000LL) __trap();
-  }
-}
-// true on exactly one lane of a fully converged warp; keeps the surrounding values warp-uniform so the
-// compiler can hold descriptors in uniform registers instead of serialising over lanes
-RCB_DEVINL bool elect_one() {
-  uint32_t pred;
-  asm volatile(
-      "{\n\t.reg .pred P;\n\t"
-      "elect.sync _|P, 0xffffffff;\n\t"
-      "selp.u32 %0, 1, 0, P;\n\t}"
-      : "=r"(pred));
-  return pred != 0;
-}
-// mbar_wait that adds the cycles spent waiting to *acc (profiling builds of the launch only)
-RCB_DEVINL void mbar_wait_t(uint32_t bar, uint32_t parity, long long* acc) {
-  if (acc == nullptr) { mbar_wait(bar, parity); return; }
-  const long long t0 = clock64();
-  mbar_wait(bar, parity);
-  *acc += clock64() - t0;
-}
-RCB_DEVINL void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-RCB_DEVINL void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-RCB_DEVINL void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-RCB_DEVINL void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-RCB_DEVINL void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-RCB_DEVINL void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-RCB_DEVINL void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
-  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map),
-               "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-               : "memory");
-}
-RCB_DEVINL void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N>
-RCB_DEVINL void tma_store_wait_read() {
-  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
-}
-RCB_DEVINL void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 RCB_DEVINL void tmem_alloc(uint32_t slot_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(ncols)
@@ -544,7 +467,9 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
               fence_proxy_async_smem();
               __syncwarp();
               if (lane == 0 && !(p.debug_skip & 1)) {
-                tma_store_4d(&map_l0, smem_u32(sb), ((x0 >> 2) + 2 * half) * 16, (yy >> 2), q_w, uc.b);
+                // debug bit 512: alias all queries onto 128 planes so the stores stay L2-resident (no DRAM writes)
+                tma_store_4d(&map_l0, smem_u32(sb), ((x0 >> 2) + 2 * half) * 16, (yy >> 2),
+                             (p.debug_skip & 512) ? (q_w & 127) : q_w, (p.debug_skip & 512) ? 0 : uc.b);
                 tma_store_commit();
               }
               ++nstore;
@@ -669,27 +594,6 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 }
 
 // ---- host side -------------------------------------------------------------------------------
-static PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
-  static PFN_cuTensorMapEncodeTiled_v12000 fn = []() -> PFN_cuTensorMapEncodeTiled_v12000 {
-    void* f = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPointByVersion("cuTensorMapEncodeTiled", &f, 12000, cudaEnableDefault, &qres) != cudaSuccess ||
-        qres != cudaDriverEntryPointSuccess)
-      return nullptr;
-    return reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(f);
-  }();
-  return fn;
-}
-
-static bool encode(CUtensorMap* m, CUtensorMapDataType dt, int rank, const void* base, const cuuint64_t* dims,
-                   const cuuint64_t* strides_bytes, const cuuint32_t* box, CUtensorMapSwizzle sw) {
-  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult r = encode_fn()(m, dt, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS;
-}
-
 }  // namespace tc
 
 static int padded_k(int C) { return (C + tc::BK - 1) / tc::BK * tc::BK; }

@@ -18,7 +18,10 @@
 //   store = one instruction writes 4 channels x 8 consecutive queries (full 32-byte sectors).
 // The kernel is bound by the L1/shared-memory pipe, so the mappings above are chosen to
 // minimise cache lines per copy instruction and shared-memory wavefronts per output.
+#include <cstdlib>
+
 #include "rcb_common.cuh"
+#include "tma_util.cuh"
 
 namespace rcb {
 
@@ -198,6 +201,167 @@ lookup_f32_kernel(PyramidDev pyr, const float* __restrict__ coords, float* __res
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// TMA gather variant (default).  The window of one (query, level) is exactly a box of whole 64-byte tiles:
+// ny tile rows x nx tiles, nx/ny = 3 or 4 at r = 4 depending on the window's phase inside the tile grid.  One
+// cp.async.bulk.tensor per query fetches it -- 3..4 contiguous runs of 192..256 bytes -- straight into shared
+// memory: address generation, the zeros padding outside the plane (TMA out-of-bounds fill) and the data
+// movement cost no registers, no LSU instructions and no L1 data-pipe wavefronts, which is what bounded the
+// register-staged kernel above (ncu: L1 data pipe 72 % busy, DRAM 43 %).  Four tensor maps per level (the
+// nx x ny combinations) live in a host-side plan that is encoded once per pyramid, not per call.
+//   CTA   = 32 consecutive queries of ONE level, 128 threads, a warp owns 8 queries end to end: lane 4i issues
+//           the box of query i on the warp's own mbarrier, the warp waits, then does the math; several CTAs per
+//           SM keep ~100 KB of gathers in flight.
+//   math  = the 4 lanes of a query split the (2r+1) y offsets; a lane reads its 3-4 window rows as whole tile
+//           rows (LDS.128), aligns them to the window's 4-byte phase with two select stages, applies the separable
+//           bilinear weights horizontally, then vertically against the previous row.
+//   store = one instruction writes 4 channels x 8 consecutive queries (full 32-byte sectors).
+// Padding INSIDE edge tiles (rows >= H_l, columns >= W_l of the last tile row/column) is unspecified in the
+// layout, so those taps are masked here; everything outside the tile grid is zero-filled by the TMA unit.
+// ---------------------------------------------------------------------------------------------
+struct LookupMaps {
+  CUtensorMap m[RCB_MAX_LEVELS * 4];  // [level][ny_sel * 2 + nx_sel]
+};
+
+struct LookupPlan {  // host-side blob behind rcb_corr_lookup_plan_*
+  LookupMaps maps;
+  rcb_pyramid_layout lay;
+  const void* ptr[RCB_MAX_LEVELS];
+  int B, H, W, radius;
+  uint32_t magic;
+};
+constexpr uint32_t kPlanMagic = 0x52434250u;  // "RCBP"
+
+template <int R>
+struct TmaCfg {
+  static constexpr int RD = 2 * R + 1;
+  static constexpr int ROWS = 2 * R + 2;
+  static constexpr int NMIN = (ROWS + 3) >> 2;  // tiles per axis a window overlaps: NMIN or NMIN + 1
+  static constexpr int NMAX = (ROWS + 6) >> 2;
+  static constexpr int SLOT_BYTES = (NMAX * NMAX * 64 + 127) / 128 * 128;  // TMA destinations are 128-byte aligned
+  static constexpr int SLOT16 = SLOT_BYTES / 16;
+  static constexpr int NBMAX = (RD + 3) / 4;    // output rows per lane
+  static constexpr int QT = 32, THREADS = 128;
+};
+
+template <int R>
+__global__ void __launch_bounds__(TmaCfg<R>::THREADS, 6)
+lookup_tma_kernel(const __grid_constant__ LookupMaps maps, PyramidDev pyr, const float* __restrict__ coords,
+                  float* __restrict__ out, int Q, int L) {
+  using Cfg = TmaCfg<R>;
+  constexpr int RD = Cfg::RD, ROWS = Cfg::ROWS, NMIN = Cfg::NMIN, NMAX = Cfg::NMAX, SLOT16 = Cfg::SLOT16;
+  constexpr int NBMAX = Cfg::NBMAX, QT = Cfg::QT;
+  __shared__ __align__(128) float4 slots[QT * SLOT16];
+  __shared__ __align__(8) unsigned long long bars[Cfg::THREADS / 32];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int l = blockIdx.y;
+  const int b = blockIdx.z;
+  const int ql = tid >> 2, sub = tid & 3;
+  const int q = blockIdx.x * QT + ql;
+  const bool q_ok = q < Q;
+  // (selects instead of pyr.H[l]: a dynamically indexed by-value parameter array is copied to local memory)
+  const int Hl = l == 0 ? pyr.H[0] : l == 1 ? pyr.H[1] : l == 2 ? pyr.H[2] : pyr.H[3];
+  const int Wl = l == 0 ? pyr.W[0] : l == 1 ? pyr.W[1] : l == 2 ? pyr.W[2] : pyr.W[3];
+  float cx = -1.0e6f, cy = -1.0e6f;
+  if (q_ok) {
+    cx = __ldg(coords + (long long)(b * 2 + 0) * Q + q);
+    cy = __ldg(coords + (long long)(b * 2 + 1) * Q + q);
+  }
+  const LevelCoord lc = level_coord<R>(cx, cy, l, Hl, Wl);
+  const int ph = lc.xs & 3, py = lc.ys & 3;
+  const int nx = (ph + ROWS + 3) >> 2, ny = (py + ROWS + 3) >> 2;
+
+  const uint32_t bar = smem_u32(&bars[warp]);
+  if (lane == 0) {
+    mbar_init(bar, 8);
+    fence_barrier_init();
+  }
+  __syncwarp();
+  if (sub == 0) {
+    if (q_ok) {
+      mbar_expect_tx(bar, (uint32_t)(nx * ny * 64));
+      tma_load_3d(smem_u32(slots + ql * SLOT16), &maps.m[l * 4 + (ny - NMIN) * 2 + (nx - NMIN)], bar,
+                  (lc.xs >> 2) * 16, lc.ys >> 2, b * Q + q);
+    } else {
+      mbar_arrive(bar);
+    }
+  }
+  if (!q_ok) return;
+  const float fx = lc.fx, fy = lc.fy, gx = 1.0f - lc.fx, gy = 1.0f - lc.fy;
+  const int b0 = (RD * sub) >> 2, nb = ((RD * (sub + 1)) >> 2) - b0;  // output rows [b0, b0 + nb), nb <= NBMAX
+  float* o = out + (((long long)b * L + l) * RD * RD + b0) * Q + q;   // channel = a * RD + b
+  const long long sa = (long long)RD * Q;
+  const float4* slot = slots + ql * SLOT16;
+  const bool ragged_w = (Wl & 3) != 0;
+  mbar_wait(bar, 0);
+
+  float hp[RD];
+#pragma unroll
+  for (int jj = 0; jj <= NBMAX; ++jj) {
+    if (jj > nb) break;
+    const int j = b0 + jj;     // window row
+    const int ya = py + j;     // row inside the fetched box
+    const bool row_ok = lc.ys + j < Hl;  // rows < 0 lie in tile rows the TMA zero-filled
+    const float4* rowp = slot + ((ya >> 2) * nx) * 4 + (ya & 3);
+    float w[4 * NMAX];
+#pragma unroll
+    for (int k = 0; k < NMAX; ++k) {
+      float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row_ok && k < nx) u = rowp[k * 4];
+      w[4 * k + 0] = u.x; w[4 * k + 1] = u.y; w[4 * k + 2] = u.z; w[4 * k + 3] = u.w;
+    }
+    float v1[ROWS + 2];
+#pragma unroll
+    for (int i = 0; i < ROWS + 2; ++i) v1[i] = (ph & 1) ? w[i + 1] : w[i];
+    float t[ROWS];
+#pragma unroll
+    for (int i = 0; i < ROWS; ++i) t[i] = (ph & 2) ? v1[i + 2] : v1[i];
+    if (ragged_w) {
+#pragma unroll
+      for (int i = 0; i < ROWS; ++i)
+        if (lc.xs + i >= Wl) t[i] = 0.f;
+    }
+    float h[RD];
+#pragma unroll
+    for (int a = 0; a < RD; ++a) h[a] = gx * t[a] + fx * t[a + 1];
+    if (jj > 0) {
+#pragma unroll
+      for (int a = 0; a < RD; ++a) o[a * sa] = gy * hp[a] + fy * h[a];
+      o += Q;
+    }
+#pragma unroll
+    for (int a = 0; a < RD; ++a) hp[a] = h[a];
+  }
+}
+
+static int plan_init(LookupPlan* plan, const void* const* pyr, const rcb_pyramid_layout& lay, int B, int H, int W,
+                     int radius) {
+  if (!encode_fn()) return RCB_ERR_NO_DEVICE;
+  const int rows = 2 * radius + 2, nmin = (rows + 3) >> 2;
+  const long long planes = (long long)B * H * W;
+  for (int l = 0; l < lay.levels; ++l) {
+    for (int sel = 0; sel < 4; ++sel) {
+      const int nx = nmin + (sel & 1), ny = nmin + (sel >> 1);
+      cuuint64_t dims[3] = {(cuuint64_t)lay.tiles_x[l] * 16, (cuuint64_t)lay.tiles_y[l], (cuuint64_t)planes};
+      cuuint64_t str[2] = {(cuuint64_t)lay.tiles_x[l] * 64, (cuuint64_t)lay.plane_stride[l] * 4};
+      cuuint32_t box[3] = {(cuuint32_t)nx * 16, (cuuint32_t)ny, 1};
+      if (!encode(&plan->maps.m[l * 4 + sel], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, pyr[l], dims, str, box,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE))
+        return RCB_ERR_INVALID_ARGUMENT;
+    }
+    plan->ptr[l] = pyr[l];
+  }
+  for (int l = lay.levels; l < RCB_MAX_LEVELS; ++l) {
+    plan->ptr[l] = nullptr;
+    for (int sel = 0; sel < 4; ++sel) plan->maps.m[l * 4 + sel] = plan->maps.m[0];
+  }
+  plan->lay = lay;
+  plan->B = B; plan->H = H; plan->W = W; plan->radius = radius;
+  plan->magic = kPlanMagic;
+  return RCB_OK;
+}
+
 template <int R>
 static int launch_lookup_r(const PyramidDev& pd, const float* coords, float* out, int B, int H, int W, int L,
                            cudaStream_t s) {
@@ -208,17 +372,57 @@ static int launch_lookup_r(const PyramidDev& pd, const float* coords, float* out
   return launch_status();
 }
 
+template <int R>
+static int launch_lookup_tma_r(const LookupPlan& plan, const PyramidDev& pd, const float* coords, float* out,
+                               cudaStream_t s) {
+  using Cfg = TmaCfg<R>;
+  const int Q = plan.H * plan.W;
+  dim3 grid((Q + Cfg::QT - 1) / Cfg::QT, plan.lay.levels, plan.B);
+  lookup_tma_kernel<R><<<grid, Cfg::THREADS, 0, s>>>(plan.maps, pd, coords, out, Q, plan.lay.levels);
+  return launch_status();
+}
+
+size_t lookup_plan_bytes() { return sizeof(LookupPlan); }
+
+int lookup_plan_init(void* plan, size_t plan_bytes, const void* const* pyr, const rcb_pyramid_layout& lay, int B,
+                     int H, int W, int radius) {
+  if (!plan || plan_bytes < sizeof(LookupPlan) || (reinterpret_cast<uintptr_t>(plan) & 63))
+    return RCB_ERR_INVALID_ARGUMENT;
+  if (lay.dtype != RCB_F32) return RCB_ERR_UNSUPPORTED;
+  return plan_init(static_cast<LookupPlan*>(plan), pyr, lay, B, H, W, radius);
+}
+
+int launch_lookup_planned(const void* plan_, const float* coords, float* out, cudaStream_t s) {
+  const LookupPlan* plan = static_cast<const LookupPlan*>(plan_);
+  if (!plan || (reinterpret_cast<uintptr_t>(plan_) & 63) || plan->magic != kPlanMagic) return RCB_ERR_INVALID_ARGUMENT;
+  const PyramidDev pd = make_pyramid_dev(plan->ptr, plan->lay);
+  static const bool legacy = [] { const char* e = getenv("RCB_LOOKUP_LEGACY"); return e && e[0] == '1'; }();
+  if (legacy) {
+    switch (plan->radius) {
+      case 1: return launch_lookup_r<1>(pd, coords, out, plan->B, plan->H, plan->W, plan->lay.levels, s);
+      case 2: return launch_lookup_r<2>(pd, coords, out, plan->B, plan->H, plan->W, plan->lay.levels, s);
+      case 3: return launch_lookup_r<3>(pd, coords, out, plan->B, plan->H, plan->W, plan->lay.levels, s);
+      case 4: return launch_lookup_r<4>(pd, coords, out, plan->B, plan->H, plan->W, plan->lay.levels, s);
+      default: return RCB_ERR_UNSUPPORTED;
+    }
+  }
+  switch (plan->radius) {
+    case 1: return launch_lookup_tma_r<1>(*plan, pd, coords, out, s);
+    case 2: return launch_lookup_tma_r<2>(*plan, pd, coords, out, s);
+    case 3: return launch_lookup_tma_r<3>(*plan, pd, coords, out, s);
+    case 4: return launch_lookup_tma_r<4>(*plan, pd, coords, out, s);
+    default: return RCB_ERR_UNSUPPORTED;
+  }
+}
+
+// Unplanned entry: encodes the tensor maps on every call (a few microseconds of host time).
 int launch_lookup(const void* const* pyr, const rcb_pyramid_layout& lay, const float* coords, float* out, int B,
                   int H, int W, int radius, cudaStream_t s) {
   if (lay.dtype != RCB_F32) return RCB_ERR_UNSUPPORTED;
-  const PyramidDev pd = make_pyramid_dev(pyr, lay);
-  switch (radius) {
-    case 1: return launch_lookup_r<1>(pd, coords, out, B, H, W, lay.levels, s);
-    case 2: return launch_lookup_r<2>(pd, coords, out, B, H, W, lay.levels, s);
-    case 3: return launch_lookup_r<3>(pd, coords, out, B, H, W, lay.levels, s);
-    case 4: return launch_lookup_r<4>(pd, coords, out, B, H, W, lay.levels, s);
-    default: return RCB_ERR_UNSUPPORTED;
-  }
+  alignas(64) LookupPlan plan;
+  const int st = plan_init(&plan, pyr, lay, B, H, W, radius);
+  if (st != RCB_OK) return st;
+  return launch_lookup_planned(&plan, coords, out, s);
 }
 
 // ---------------------------------------------------------------------------------------------

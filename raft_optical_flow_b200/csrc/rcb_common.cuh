@@ -113,6 +113,10 @@ int launch_build_tc(const float* f1, const float* f2, void* const* pyr, const rc
                     int C, int H, int W, int mode, void* ws, size_t ws_bytes, cudaStream_t s);
 int launch_lookup(const void* const* pyr, const rcb_pyramid_layout& lay, const float* coords, float* out, int B,
                   int H, int W, int radius, cudaStream_t s);
+size_t lookup_plan_bytes();
+int lookup_plan_init(void* plan, size_t plan_bytes, const void* const* pyr, const rcb_pyramid_layout& lay, int B,
+                     int H, int W, int radius);
+int launch_lookup_planned(const void* plan, const float* coords, float* out, cudaStream_t s);
 int launch_lookup_backward(const void* const* pyr, const rcb_pyramid_layout& lay, const float* coords,
                            const float* grad_out, float* const* dpyr, float* dcoords, int B, int H, int W,
                            int radius, cudaStream_t s);
