@@ -27,14 +27,14 @@ def header_symbols():
 
 def test_library_exports_every_declared_symbol(lib):
     syms = header_symbols()
-    assert len(syms) == 13
+    assert len(syms) == 16
     for s in syms:
         assert hasattr(lib, s), s
     assert sorted(_cabi.SIGNATURES) == syms  # the ctypes table binds exactly the header
 
 
 def test_status_strings(lib):
-    assert lib.rcb_abi_version() == 2
+    assert lib.rcb_abi_version() == 3
     assert lib.rcb_status_string(0) == b"ok"
     assert b"invalid" in lib.rcb_status_string(-1)
     assert b"unsupported" in lib.rcb_status_string(-2)
@@ -67,6 +67,12 @@ def test_entry_points_validate_before_touching_the_device(lib):
     assert lib.rcb_corr_lookup(null, None, None, 1, 8, 8, 4, 4, 0, None) == -1
     assert lib.rcb_corr_build(None, None, null, 1, 8, 8, 8, 4, 0, 0, None, 0, None) == -1
     assert lib.rcb_altcorr_forward(None, None, None, None, 1, 1, 8, 8, 8, 8, 8, 4, None) == -1
+    assert lib.rcb_corr_lookup_plan_bytes() >= 16 * 128  # four tensor maps per level
+    assert lib.rcb_corr_lookup_plan_init(None, 0, null, 1, 8, 8, 4, 4, 0) == -1
+    assert lib.rcb_corr_lookup_planned(None, None, None, None) == -1
+    blob = (ctypes.c_char * (lib.rcb_corr_lookup_plan_bytes() + 64))()
+    plan = (ctypes.addressof(blob) + 63) & ~63
+    assert lib.rcb_corr_lookup_planned(plan, ctypes.addressof(blob), ctypes.addressof(blob), None) == -1  # not initialised
     buf = (ctypes.c_float * 64)()
     p = ctypes.addressof(buf)
     assert lib.rcb_altcorr_forward(p, p, p, p, 1, 1, 2, 2, 2, 2, 4, 9, None) == -2  # radius > RCB_MAX_RADIUS
