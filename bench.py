@@ -314,7 +314,7 @@ def run_ours(args, cfg):
                 "note": "pinned host fmaps+coords -> CorrBlock(...)(coords) x iters -> last corr tensor to pinned host; "
                         "copies of neighbouring steps overlap the kernels on separate streams"},
         "gpu_launches": args.steps * (launches_build + iters),
-        "roofline": {"kernel": "lookup_f32_kernel<4>", "bound": "hbm", "achieved": lookup_gbs, "peak": hbm_peak,
+        "roofline": {"kernel": "lookup_tma_kernel<4>", "bound": "hbm", "achieved": lookup_gbs, "peak": hbm_peak,
                      "unit": "GB/s", "frac": lookup_gbs / hbm_peak, "traffic": ncu_traffic("lookup"),
                      "peak_source": peak_kind, "us_per_launch": lookup_ms * 1e3,
                      "algorithmic_bytes_per_launch": lookup_bytes},

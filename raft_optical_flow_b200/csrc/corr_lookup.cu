@@ -5,50 +5,30 @@
 // (2r+2)^2 tap window is gathered from that query's correlation plane and bilinearly resampled to the
 // (2r+1)^2 outputs the update block consumes.  HBM-bound gather: see DESIGN.md "K2".
 //
-// Work decomposition
-//   CTA   = 32 consecutive query pixels in flattened (h, w) order of ONE level; 4 threads per query; a
-//           warp owns 8 queries end to end, so there is no block-level barrier.  ~21 KB of shared memory.
-//   fetch = 16-byte cp.async (L2-only, zero-fill): out-of-plane rows/chunks are zero-filled by the copy
-//           itself, which IS the zeros-padding of grid_sample.  Planes are stored as 4x4 tiles of 64 bytes
-//           (one DRAM atom), so a (2r+2)^2 window touches ~3.25^2 atoms instead of ~1.6 per row; the copy
-//           un-tiles into row-major window rows in shared memory.
-//   math  = the 4 lanes of a query split the (2r+1) x offsets; two LDS.128 per window row and lane, two
-//           select stages for the 4-byte phase, separable bilinear weights (all (2r+1)^2 samples of one
-//           level share the same fractional offset because the window offsets are integers).
+// The window of one (query, level) is exactly a box of whole 64-byte tiles of the pyramid layout:
+// ny tile rows x nx tiles, nx/ny = 3 or 4 at r = 4 depending on the window's phase inside the tile grid.  One
+// cp.async.bulk.tensor (TMA) per query fetches it -- 3..4 contiguous runs of 192..256 bytes -- straight into
+// shared memory: address generation, the zeros padding outside the plane (TMA out-of-bounds fill) and the data
+// movement cost no registers, no LSU instructions and no L1 data-pipe wavefronts (an earlier register-staged
+// version of this kernel was bound by exactly those: ncu L1 data pipe 72 % busy, DRAM 43 %; this one runs at
+// ~80 % of the measured copy bandwidth for the bytes it really moves).  Four tensor maps per level (the nx x ny
+// combinations) live in a host-side plan that is encoded once per pyramid, not per call.
+//   CTA   = 32 consecutive queries of ONE level, 128 threads, a warp owns 8 queries end to end: lane 4i issues
+//           the box of query i on the warp's own mbarrier, the warp waits, then does the math; six CTAs per SM
+//           keep ~100 KB of gathers in flight.
+//   math  = the 4 lanes of a query split the (2r+1) y offsets; a lane reads its 3-4 window rows as whole tile
+//           rows (LDS.128), aligns them to the window's 4-byte phase with two select stages, applies the separable
+//           bilinear weights horizontally, then vertically against the previous row (all (2r+1)^2 samples of a
+//           level share one fractional offset because the window offsets are integers).
 //   store = one instruction writes 4 channels x 8 consecutive queries (full 32-byte sectors).
-// The kernel is bound by the L1/shared-memory pipe, so the mappings above are chosen to
-// minimise cache lines per copy instruction and shared-memory wavefronts per output.
+// Padding INSIDE edge tiles (rows >= H_l, columns >= W_l of the last tile row/column) is unspecified in the
+// layout, so those taps are masked here; everything outside the tile grid is zero-filled by the TMA unit.
 #include <cstdlib>
 
 #include "rcb_common.cuh"
 #include "tma_util.cuh"
 
 namespace rcb {
-
-template <int R>
-struct LookupCfg {
-  static constexpr int RD = 2 * R + 1;
-  static constexpr int ROWS = 2 * R + 2;           // taps per axis
-  static constexpr int NCH = (ROWS + 3 + 3) / 4;   // 16-byte chunks covering ROWS floats at any 4-byte phase
-  // Shared-memory window of one query: ROWS rows of RS 16-byte units (RS odd), queries S units apart with
-  // S = 4 (mod 8).  With these strides both access patterns of a quarter warp (2 queries x 4 lanes) are free of
-  // bank conflicts: the fetch writes 4 consecutive rows of one chunk column per query (bank groups
-  // {0,RS,2RS,3RS} and the same +4), the math reads 1-3 neighbouring chunks of one row per query.
-  static constexpr int RS = NCH | 1;
-  static constexpr int BLK16 = (ROWS * RS + 3) / 8 * 8 + 4;
-  static constexpr int QT = 32;                    // queries per CTA
-  static constexpr int THREADS = 128;
-  static_assert(BLK16 >= ROWS * RS && (BLK16 & 7) == 4, "query stride must be 4 mod 8 sixteen-byte units");
-};
-
-// streaming 16-byte load: read-only path, do not allocate in L1
-RCB_DEVINL float4 ld_nc_f4(const float* p) {
-  float4 v;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
-               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-               : "l"(p));
-  return v;
-}
 
 struct LevelCoord {
   int xs, ys;    // integer position of tap (0,0)
@@ -72,153 +52,6 @@ RCB_DEVINL LevelCoord level_coord(float cx, float cy, int l, int Hl, int Wl) {
   return c;
 }
 
-template <int R>
-__global__ void __launch_bounds__(LookupCfg<R>::THREADS)
-lookup_f32_kernel(PyramidDev pyr, const float* __restrict__ coords, float* __restrict__ out, int Q, int L) {
-  using Cfg = LookupCfg<R>;
-  constexpr int RD = Cfg::RD, ROWS = Cfg::ROWS, NCH = Cfg::NCH, RS = Cfg::RS, BLK16 = Cfg::BLK16, QT = Cfg::QT;
-  __shared__ float4 win[QT * BLK16];  // one level of 32 query windows, row-major rows of RS 16-byte units
-
-  const int tid = threadIdx.x, lane = tid & 31;
-  const int l = blockIdx.y;
-  const int b = blockIdx.z;
-  const int q0 = blockIdx.x * QT;
-  const int Hl = pyr.H[l], Wl = pyr.W[l], tw = pyr.tiles_x[l];
-  const long long ps = pyr.plane_stride[l];
-  const float* __restrict__ base = static_cast<const float*>(pyr.ptr[l]);
-
-  // Thread t serves query q0 + t/4 in BOTH phases, so a warp only ever touches the windows of its own
-  // 8 queries: no block-level barrier, the 4 warps of the CTA run independently.
-  const int ql = tid >> 2;   // query within the CTA
-  const int sub = tid & 3;   // fetch: row inside a 4x4 tile; math: group of x offsets
-  const int q = q0 + ql;
-  const bool q_ok = q < Q;
-  float cx = -1.0e6f, cy = -1.0e6f;  // queries past the end fetch nothing and store nothing
-  if (q_ok) {
-    cx = __ldg(coords + (long long)(b * 2 + 0) * Q + q);
-    cy = __ldg(coords + (long long)(b * 2 + 1) * Q + q);
-  }
-  const LevelCoord lc = level_coord<R>(cx, cy, l, Hl, Wl);
-  const int ph = lc.xs & 3;
-  float4* blk = win + ql * BLK16;
-
-  // ---- fetch: 16-byte loads through registers, un-tiling on the fly --------------------------------
-  // Lane (query, r) loads row r of every 4x4 tile the window overlaps: the 4 lanes of a query cover one
-  // whole 64-byte tile per instruction, which the L1 tag stage turns into ONE two-sector request (cp.async.cg
-  // would issue one request per lane: the kernel is bound by the L1->L2 request port).
-  // All loads of a thread are issued before the first use.  Rows/chunks outside the plane stay zero, which
-  // IS the zeros padding of grid_sample; tile rows outside the window and chunks the window does not reach
-  // are not fetched at all.
-  if (q_ok) {
-    const int xa = lc.xs - ph;         // first chunk column (multiple of 4, may be negative)
-    const int ty0 = lc.ys >> 2;        // first tile row (arithmetic shift: floor)
-    const int nchunk = (ph + ROWS + 3) >> 2;
-    const float* plane = base + ((long long)b * Q + q) * ps;
-    int coff[NCH], cvalid[NCH];        // per chunk column: offset of its tile inside a tile row, valid floats
-#pragma unroll
-    for (int c = 0; c < NCH; ++c) {
-      const int xc = xa + 4 * c;
-      const bool ok = (c < nchunk) && (xc >= 0) && (xc < Wl);
-      coff[c] = ok ? (xc >> 2) << 4 : 0;
-      cvalid[c] = ok ? min(4, Wl - xc) : (c < nchunk ? 0 : -1);  // -1: the window does not reach this chunk
-    }
-    constexpr int NTI = (ROWS + 3 + 3) / 4;  // tile rows a window can overlap
-    float4 v[NTI][NCH];
-    int jrow[NTI];
-#pragma unroll
-    for (int ti = 0; ti < NTI; ++ti) {
-      const int y = ((ty0 + ti) << 2) + sub;
-      const int j = y - lc.ys;
-      jrow[ti] = (j >= 0 && j < ROWS) ? j : -1;
-      const bool y_ok = (jrow[ti] >= 0) && (y >= 0) && (y < Hl);
-      const float* trow = plane + (((long long)(y >> 2) * tw) << 4) + ((y & 3) << 2);
-#pragma unroll
-      for (int c = 0; c < NCH; ++c) {
-        v[ti][c] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (y_ok && cvalid[c] > 0) v[ti][c] = ld_nc_f4(trow + coff[c]);
-      }
-    }
-    if (Wl & 3) {  // the last chunk of a row may hang over the right edge: zero the overhang
-#pragma unroll
-      for (int c = 0; c < NCH; ++c) {
-        if (cvalid[c] > 0 && cvalid[c] < 4) {
-#pragma unroll
-          for (int ti = 0; ti < NTI; ++ti) {
-            if (cvalid[c] < 2) v[ti][c].y = 0.f;
-            if (cvalid[c] < 3) v[ti][c].z = 0.f;
-            v[ti][c].w = 0.f;
-          }
-        }
-      }
-    }
-#pragma unroll
-    for (int ti = 0; ti < NTI; ++ti) {
-      if (jrow[ti] < 0) continue;
-#pragma unroll
-      for (int c = 0; c < NCH; ++c)
-        if (cvalid[c] >= 0) blk[jrow[ti] * RS + c] = v[ti][c];
-    }
-  }
-  __syncwarp();
-
-  // ---- math + store: lane = (query, group of x offsets) ------------------------------------------
-  // The (2r+1) x offsets are split over the 4 lanes of a query; a lane needs at most 4 consecutive taps of
-  // every window row = two 16-byte chunks (LDS.128 x2, the 4 lanes of a query mostly share addresses), aligns
-  // them with two select stages and applies the separable bilinear weights (all samples of one level share the
-  // same fractional offset).  A store instruction writes 4 channels x 8 consecutive queries (32-byte sectors).
-  if (!q_ok) return;
-  const int a0 = (RD * sub) >> 2, a1 = (RD * (sub + 1)) >> 2;  // x offsets [a0, a1)
-  const int na = a1 - a0;                                      // <= 3
-  const int start = ph + a0;
-  const int k0 = start >> 2, off = start & 3;
-  const int k1 = min(k0 + 1, NCH - 1);
-  const float fx = lc.fx, fy = lc.fy, gx = 1.0f - lc.fx, gy = 1.0f - lc.fy;
-  float* o = out + (((long long)b * L + l) * RD * RD + (long long)a0 * RD) * Q + q;
-  const long long sa = (long long)RD * Q;  // channel stride of one x offset
-  float prev[3] = {0.f, 0.f, 0.f};
-#pragma unroll
-  for (int j = 0; j < ROWS; ++j) {
-    const float4 u0 = blk[j * RS + k0];
-    const float4 u1 = blk[j * RS + k1];
-    const float w[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
-    float v1[6];
-#pragma unroll
-    for (int i = 0; i < 6; ++i) v1[i] = (off & 1) ? w[i + 1] : w[i];
-    float sv[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) sv[i] = (off & 2) ? v1[i + 2] : v1[i];
-    float t[3];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) t[i] = gx * sv[i] + fx * sv[i + 1];
-    if (j > 0) {
-#pragma unroll
-      for (int i = 0; i < 3; ++i)
-        if (i < na) o[i * sa] = gy * prev[i] + fy * t[i];
-      o += Q;
-    }
-#pragma unroll
-    for (int i = 0; i < 3; ++i) prev[i] = t[i];
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
-// TMA gather variant (default).  The window of one (query, level) is exactly a box of whole 64-byte tiles:
-// ny tile rows x nx tiles, nx/ny = 3 or 4 at r = 4 depending on the window's phase inside the tile grid.  One
-// cp.async.bulk.tensor per query fetches it -- 3..4 contiguous runs of 192..256 bytes -- straight into shared
-// memory: address generation, the zeros padding outside the plane (TMA out-of-bounds fill) and the data
-// movement cost no registers, no LSU instructions and no L1 data-pipe wavefronts, which is what bounded the
-// register-staged kernel above (ncu: L1 data pipe 72 % busy, DRAM 43 %).  Four tensor maps per level (the
-// nx x ny combinations) live in a host-side plan that is encoded once per pyramid, not per call.
-//   CTA   = 32 consecutive queries of ONE level, 128 threads, a warp owns 8 queries end to end: lane 4i issues
-//           the box of query i on the warp's own mbarrier, the warp waits, then does the math; several CTAs per
-//           SM keep ~100 KB of gathers in flight.
-//   math  = the 4 lanes of a query split the (2r+1) y offsets; a lane reads its 3-4 window rows as whole tile
-//           rows (LDS.128), aligns them to the window's 4-byte phase with two select stages, applies the separable
-//           bilinear weights horizontally, then vertically against the previous row.
-//   store = one instruction writes 4 channels x 8 consecutive queries (full 32-byte sectors).
-// Padding INSIDE edge tiles (rows >= H_l, columns >= W_l of the last tile row/column) is unspecified in the
-// layout, so those taps are masked here; everything outside the tile grid is zero-filled by the TMA unit.
-// ---------------------------------------------------------------------------------------------
 struct LookupMaps {
   CUtensorMap m[RCB_MAX_LEVELS * 4];  // [level][ny_sel * 2 + nx_sel]
 };
@@ -247,7 +80,7 @@ struct TmaCfg {
 template <int R>
 __global__ void __launch_bounds__(TmaCfg<R>::THREADS, 6)
 lookup_tma_kernel(const __grid_constant__ LookupMaps maps, PyramidDev pyr, const float* __restrict__ coords,
-                  float* __restrict__ out, int Q, int L) {
+                  float* __restrict__ out, int Q, int L, int dbg) {
   using Cfg = TmaCfg<R>;
   constexpr int RD = Cfg::RD, ROWS = Cfg::ROWS, NMIN = Cfg::NMIN, NMAX = Cfg::NMAX, SLOT16 = Cfg::SLOT16;
   constexpr int NBMAX = Cfg::NBMAX, QT = Cfg::QT;
@@ -279,7 +112,7 @@ lookup_tma_kernel(const __grid_constant__ LookupMaps maps, PyramidDev pyr, const
   }
   __syncwarp();
   if (sub == 0) {
-    if (q_ok) {
+    if (q_ok && !(dbg & 2)) {
       mbar_expect_tx(bar, (uint32_t)(nx * ny * 64));
       tma_load_3d(smem_u32(slots + ql * SLOT16), &maps.m[l * 4 + (ny - NMIN) * 2 + (nx - NMIN)], bar,
                   (lc.xs >> 2) * 16, lc.ys >> 2, b * Q + q);
@@ -295,6 +128,7 @@ lookup_tma_kernel(const __grid_constant__ LookupMaps maps, PyramidDev pyr, const
   const float4* slot = slots + ql * SLOT16;
   const bool ragged_w = (Wl & 3) != 0;
   mbar_wait(bar, 0);
+  if (dbg & 1) return;  // timing experiment: gather only
 
   float hp[RD];
 #pragma unroll
@@ -363,22 +197,13 @@ static int plan_init(LookupPlan* plan, const void* const* pyr, const rcb_pyramid
 }
 
 template <int R>
-static int launch_lookup_r(const PyramidDev& pd, const float* coords, float* out, int B, int H, int W, int L,
-                           cudaStream_t s) {
-  using Cfg = LookupCfg<R>;
-  const int Q = H * W;
-  dim3 grid((Q + Cfg::QT - 1) / Cfg::QT, L, B);
-  lookup_f32_kernel<R><<<grid, Cfg::THREADS, 0, s>>>(pd, coords, out, Q, L);
-  return launch_status();
-}
-
-template <int R>
 static int launch_lookup_tma_r(const LookupPlan& plan, const PyramidDev& pd, const float* coords, float* out,
                                cudaStream_t s) {
   using Cfg = TmaCfg<R>;
   const int Q = plan.H * plan.W;
   dim3 grid((Q + Cfg::QT - 1) / Cfg::QT, plan.lay.levels, plan.B);
-  lookup_tma_kernel<R><<<grid, Cfg::THREADS, 0, s>>>(plan.maps, pd, coords, out, Q, plan.lay.levels);
+  static const int dbg = [] { const char* e = getenv("RCB_LOOKUP_DEBUG"); return e ? atoi(e) : 0; }();
+  lookup_tma_kernel<R><<<grid, Cfg::THREADS, 0, s>>>(plan.maps, pd, coords, out, Q, plan.lay.levels, dbg);
   return launch_status();
 }
 
@@ -396,16 +221,6 @@ int launch_lookup_planned(const void* plan_, const float* coords, float* out, cu
   const LookupPlan* plan = static_cast<const LookupPlan*>(plan_);
   if (!plan || (reinterpret_cast<uintptr_t>(plan_) & 63) || plan->magic != kPlanMagic) return RCB_ERR_INVALID_ARGUMENT;
   const PyramidDev pd = make_pyramid_dev(plan->ptr, plan->lay);
-  static const bool legacy = [] { const char* e = getenv("RCB_LOOKUP_LEGACY"); return e && e[0] == '1'; }();
-  if (legacy) {
-    switch (plan->radius) {
-      case 1: return launch_lookup_r<1>(pd, coords, out, plan->B, plan->H, plan->W, plan->lay.levels, s);
-      case 2: return launch_lookup_r<2>(pd, coords, out, plan->B, plan->H, plan->W, plan->lay.levels, s);
-      case 3: return launch_lookup_r<3>(pd, coords, out, plan->B, plan->H, plan->W, plan->lay.levels, s);
-      case 4: return launch_lookup_r<4>(pd, coords, out, plan->B, plan->H, plan->W, plan->lay.levels, s);
-      default: return RCB_ERR_UNSUPPORTED;
-    }
-  }
   switch (plan->radius) {
     case 1: return launch_lookup_tma_r<1>(*plan, pd, coords, out, s);
     case 2: return launch_lookup_tma_r<2>(*plan, pd, coords, out, s);

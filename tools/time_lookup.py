@@ -1,6 +1,7 @@
-"""Times rcb_corr_lookup_planned on a prebuilt pyramid (CUDA events on the launching stream, fresh coords per
-launch, no allocation inside the loop) and checks it against the register-staged kernel (RCB_LOOKUP_LEGACY=1 in a
-second process).   python tools/time_lookup.py [--config cfg2] [--reps 64] [--dump out.pt]"""
+"""Times rcb_corr_lookup_planned on a prebuilt pyramid (CUDA events on the launching stream, a different coords
+tensor per launch, no allocation inside the loop).  --dump / --compare save and diff the output of one launch
+across builds; RCB_LOOKUP_DEBUG=1 / 2 time the gather alone / the resampling + stores alone.
+    python tools/time_lookup.py [--config cfg2] [--reps 64] [--smooth] [--dump out.pt | --compare out.pt]"""
 import argparse, os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -10,6 +11,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--config", default="cfg2")
 ap.add_argument("--reps", type=int, default=64)
 ap.add_argument("--sigma", type=float, default=4.0)
+ap.add_argument("--smooth", action="store_true", help="smooth flow field (neighbouring queries share window phase)")
 ap.add_argument("--dump", default=None)
 ap.add_argument("--compare", default=None)
 a = ap.parse_args()
@@ -21,7 +23,12 @@ f2 = (0.75 * torch.randn(B, C, H, W, generator=g)).to(dev)
 blk = CorrBlock(f1, f2, num_levels=L, radius=r)
 ys, xs = torch.meshgrid(torch.arange(H), torch.arange(W), indexing="ij")
 grid = torch.stack([xs, ys]).float()[None]
-coords = [(grid + a.sigma * torch.randn(B, 2, H, W, generator=g)).to(dev).contiguous() for _ in range(8)]
+if a.smooth:  # slowly varying flow: a different constant + gentle ramp per set
+    ramp = torch.stack([xs.float() / W, ys.float() / H])[None]
+    coords = [(grid + torch.tensor([3.3 + i, -2.7 - 0.5 * i]).view(1, 2, 1, 1) + 2.0 * ramp).expand(B, 2, H, W).to(dev).contiguous()
+              for i in range(8)]
+else:
+    coords = [(grid + a.sigma * torch.randn(B, 2, H, W, generator=g)).to(dev).contiguous() for _ in range(8)]
 st = blk._state
 rd = 2 * r + 1
 out = torch.empty((B, L * rd * rd, H, W), device=dev)
@@ -40,7 +47,7 @@ e1.record()
 torch.cuda.synchronize()
 us = e0.elapsed_time(e1) / a.reps * 1e3
 _, lb, _ = algorithmic_bytes(B, C, H, W, r, L)
-print(f"{a.config} legacy={os.environ.get('RCB_LOOKUP_LEGACY', '0')} lookup {us:.1f} us/launch  "
+print(f"{a.config} debug={os.environ.get('RCB_LOOKUP_DEBUG', '0')} {'smooth' if a.smooth else f'sigma={a.sigma}'} lookup {us:.1f} us/launch  "
       f"{lb / us / 1e3:.0f} GB/s algorithmic = {lb / us / 1e3 / 6545.3:.3f} of HBM peak")
 call(coords[0])
 torch.cuda.synchronize()
