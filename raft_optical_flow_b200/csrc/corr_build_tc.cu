@@ -56,7 +56,7 @@ constexpr int THREADS_TS = THREADS + 32 * 4;           // + 4 warps that place A
 //   [stg_off, +32 KB)       epilogue staging, 2 x 4 KB per warp
 //   [bar_off, +1 KB)        mbarriers + TMEM base slot
 constexpr int SMEM_BUDGET = 227 * 1024;
-constexpr int STG_TOTAL = NUM_EPI_WARPS * 2 * STG_BYTES;
+constexpr int MAX_STG = 8;                 // staged store boxes per epilogue warp (ring; count chosen at launch)
 constexpr int BAR_BYTES = 1024;
 
 struct Params {
@@ -72,10 +72,12 @@ struct Params {
   float scale;      // 1 / sqrt(C)
   int direct_store; // debug: bypass the TMA stores
   int nstage, b_off, stg_off, bar_off;  // shared memory carve-up (bytes)
+  int nstg;                             // staging boxes per epilogue warp
   int nacc, acc_col0;                   // TMEM: accumulator count, first accumulator column
   int Kp;                               // padded channel count
   const uint32_t* a_pack;               // packed bf16 A operand, [part][B][Q][Kp/2] 32-bit words (TS kernel)
   unsigned long long* prof;  // debug: per-CTA cycle counters (16 per CTA), null in production
+  int seq_chunks_per_cta;  // debug bit 1024
   int debug_skip;   // debug bitmask: 1 skip L0 TMA store issue, 2 skip L1 store, 4 skip L2/L3, 8 skip staging writes
   float* pyr[RCB_MAX_LEVELS];
   int Hl[RCB_MAX_LEVELS], Wl[RCB_MAX_LEVELS], tx[RCB_MAX_LEVELS];  // level sizes, tiles per tile row
@@ -218,7 +220,7 @@ template <bool TS>
 __global__ void __launch_bounds__(TS ? THREADS_TS : THREADS, 1)
 build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                 const __grid_constant__ CUtensorMap map_l0, const __grid_constant__ CUtensorMap map_l1,
-                const Params p) {
+                const __grid_constant__ CUtensorMap map_seq, const Params p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const uint32_t smem_base = smem_u32(smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -386,8 +388,23 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     int buf = 0;
     uint32_t aph = 0;
     const int lane_q = (warp & 3) * 32;  // TMEM lane quarter this warp may access
-    unsigned char* stg = smem + p.stg_off + ew * 2 * STG_BYTES;
-    uint32_t nstore = 0;  // staged stores issued by this warp (buffer = nstore & 1)
+    const int NSTG = p.nstg;
+    unsigned char* stg = smem + p.stg_off + ew * NSTG * STG_BYTES;
+    uint32_t nstore = 0;  // staged stores issued by this warp
+    int sbuf = 0;         // staging ring position = nstore % NSTG
+    // the bulk group that last used a staging buffer is NSTG groups old: wait until at most NSTG - 1 are unread
+    auto wait_stg = [&]() {
+      if (lane == 0) {
+        switch (NSTG) {
+          case 2: tma_store_wait_read<1>(); break;
+          case 3: tma_store_wait_read<2>(); break;
+          case 4: tma_store_wait_read<3>(); break;
+          case 6: tma_store_wait_read<5>(); break;
+          default: tma_store_wait_read<7>(); break;
+        }
+      }
+      __syncwarp();
+    };
     uint32_t tile = 0;
     long long w_full = 0, w_st = 0, w_ld = 0;
     long long* pw_full = p.prof ? &w_full : nullptr;
@@ -446,11 +463,10 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
               if (x0 + 8 * half >= p.W) break;  // warp-uniform: these tiles do not exist
-              unsigned char* sb = stg + (nstore & 1) * STG_BYTES;
+              unsigned char* sb = stg + sbuf * STG_BYTES;
               {
                 const long long t0 = p.prof ? clock64() : 0;
-                if (lane == 0) tma_store_wait_read<1>();  // the store that used this buffer has been read out
-                __syncwarp();
+                wait_stg();  // the store that used this buffer has been read out
                 if (p.prof) w_st += clock64() - t0;
               }
               if (!(p.debug_skip & 8)) {
@@ -468,11 +484,17 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
               __syncwarp();
               if (lane == 0 && !(p.debug_skip & 1)) {
                 // debug bit 512: alias all queries onto 128 planes so the stores stay L2-resident (no DRAM writes)
-                tma_store_4d(&map_l0, smem_u32(sb), ((x0 >> 2) + 2 * half) * 16, (yy >> 2),
-                             (p.debug_skip & 512) ? (q_w & 127) : q_w, (p.debug_skip & 512) ? 0 : uc.b);
+                // debug bit 1024: write the boxes as consecutive 4 KB chunks (sequential DRAM pattern, wrong layout)
+                if (p.debug_skip & 1024)
+                  tma_store_2d(&map_seq, smem_u32(sb), 0,
+                               (int)(((long long)blockIdx.x * p.seq_chunks_per_cta + (nstore * NUM_EPI_WARPS + ew) % p.seq_chunks_per_cta) * 32));
+                else
+                  tma_store_4d(&map_l0, smem_u32(sb), ((x0 >> 2) + 2 * half) * 16, (yy >> 2),
+                               (p.debug_skip & 512) ? (q_w & 127) : q_w, (p.debug_skip & 512) ? 0 : uc.b);
                 tma_store_commit();
               }
               ++nstore;
+              if (++sbuf == NSTG) sbuf = 0;
             }
           }
         }
@@ -496,9 +518,8 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                   if (y1 + r < p.Hl[1] && x1 + j < p.Wl[1]) plane[tile_off(y1 + r, x1 + j, p.tx[1])] = l1[r][j];
             }
           } else if (y1 < p.Hl[1] && x1 < p.Wl[1] && q_w < p.Q && !(p.debug_skip & 2)) {
-            unsigned char* sb = stg + (nstore & 1) * STG_BYTES;
-            if (lane == 0) tma_store_wait_read<1>();
-            __syncwarp();
+            unsigned char* sb = stg + sbuf * STG_BYTES;
+            wait_stg();
 #pragma unroll
             for (int c = 0; c < 8; ++c) {  // chunk c = tile (c >> 2), tile row (c & 3)
               const int r = c & 3, col = 4 * (c >> 2);
@@ -512,6 +533,7 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
               tma_store_commit();
             }
             ++nstore;
+            if (++sbuf == NSTG) sbuf = 0;
           }
         }
         if (p.levels > 2 && q_ok && !(p.debug_skip & 4)) {
@@ -657,6 +679,19 @@ int launch_build_tc(const float* f1, const float* f2, void* const* pyr, const rc
       return RCB_ERR_INVALID_ARGUMENT;
   }
 
+  CUtensorMap map_seq = map_l0;
+  long long seq_chunks = lay.level_bytes[0] / 4096;
+  {
+    const char* skip = getenv("RCB_TC_DEBUG_SKIP");
+    if (skip && (atoi(skip) & 1024)) {
+      cuuint64_t dims[2] = {32, (cuuint64_t)seq_chunks * 32};
+      cuuint64_t str[1] = {128};
+      cuuint32_t box[2] = {32, 32};
+      if (!encode(&map_seq, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, pyr[0], dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B))
+        return RCB_ERR_INVALID_ARGUMENT;
+    }
+  }
+
   // 3. work decomposition: unit = (batch, 128-query tile, group of patches); A stays resident per unit
   Params p{};
   p.B = B; p.C = C; p.H = H; p.W = W; p.Q = Q;
@@ -698,6 +733,11 @@ int launch_build_tc(const float* f1, const float* f2, void* const* pyr, const rc
     p.nacc = MAX_ACC;
   }
   const int a_bytes = ts ? 0 : parts * p.kblocks * A_TILE_BYTES;
+  int nstg = 4;
+  if (const char* e = getenv("RCB_TC_NSTG")) nstg = atoi(e);
+  if (nstg != 2 && nstg != 3 && nstg != 4 && nstg != 6 && nstg != 8) nstg = 4;
+  p.nstg = nstg;
+  const int STG_TOTAL = NUM_EPI_WARPS * nstg * STG_BYTES;
   int nstage = (SMEM_BUDGET - BAR_BYTES - STG_TOTAL - a_bytes) / STAGE_BYTES;
   if (nstage > MAX_STAGE) nstage = MAX_STAGE;
   if (const char* ns = getenv("RCB_TC_NSTAGE")) nstage = atoi(ns) < nstage ? atoi(ns) : nstage;
@@ -709,14 +749,15 @@ int launch_build_tc(const float* f1, const float* f2, void* const* pyr, const rc
   const int smem_total = p.bar_off + BAR_BYTES;
 
   const int grid = p.units < kNumSMs ? p.units : kNumSMs;
+  p.seq_chunks_per_cta = (int)(seq_chunks / grid);
   if (ts) {
     cudaError_t e = cudaFuncSetAttribute(build_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET);
     if (e != cudaSuccess) return (int)e;
-    build_tc_kernel<true><<<grid, THREADS_TS, smem_total, s>>>(map_a, map_b, map_l0, map_l1, p);
+    build_tc_kernel<true><<<grid, THREADS_TS, smem_total, s>>>(map_a, map_b, map_l0, map_l1, map_seq, p);
   } else {
     cudaError_t e = cudaFuncSetAttribute(build_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET);
     if (e != cudaSuccess) return (int)e;
-    build_tc_kernel<false><<<grid, THREADS, smem_total, s>>>(map_a, map_b, map_l0, map_l1, p);
+    build_tc_kernel<false><<<grid, THREADS, smem_total, s>>>(map_a, map_b, map_l0, map_l1, map_seq, p);
   }
   return launch_status();
 }
