@@ -2,28 +2,43 @@
 //
 // Replaces CorrBlock.corr (reference core/corr.py:96-127: matmul + / sqrt(C)) and the avg_pool2d loop of
 // CorrBlock.__init__ (core/corr.py:52-54).  See DESIGN.md "K1" for the roofline discussion: with an fp32
-// pyramid the kernel is bound by the 2.2 GB of stores, so the design goal is to keep the tensor pipe and the
-// operand traffic below the store time and to overlap everything with the epilogue.
+// pyramid the kernel is bound by the 2.2 GB of stores, and in the 3-product fp32-parity mode the tensor pipe
+// needs about as long, so the design goal is to keep both busy at the same time.
 //
 //   pack kernel   fp32 NCHW feature maps -> bf16 K-major [part][B][Q][Kp] (part 0 = hi, part 1 = lo = x - hi),
-//                 i.e. a transpose + split.  RCB_BUILD_BF16X3 evaluates  hi*hi + hi*lo + lo*hi  (error ~2e-6 of
+//                 i.e. a transpose + split.  RCB_BUILD_BF16X3 evaluates  hi*hi + hi*lo + lo*hi  (error ~5e-6 of
 //                 max-abs); RCB_BUILD_BF16 uses the hi parts only.
-//   main kernel   persistent, warp-specialised, one CTA per SM, 192 threads:
-//     warp 0      TMA producer.  A (128 queries x Kp, hi and lo) is loaded once per work unit and stays
-//                 resident in shared memory; B tiles (an 8 x 16 PATCH of target pixels x 64 channels, fetched
-//                 as one 4-D TMA box of the [part*B, H, W, Kp] tensor, out-of-image rows/cols zero-filled)
-//                 stream through a 4-stage mbarrier ring.
-//     warp 1      MMA issuer: tcgen05.mma.cta_group::1.kind::f16, M=128, N=128, K=16, SWIZZLE_128B K-major
-//                 smem descriptors, fp32 accumulators in TMEM, 4 accumulator buffers (512 columns).
-//     warps 2-5   epilogue: tcgen05.ld (lane = query, 64 columns = 4 patch rows x 16 targets = one band of four
-//                 4x4 pyramid tiles = 256 contiguous bytes per query), scale by 1/sqrt(C); level 0 leaves
-//                 through a SWIZZLE_128B staging box and 4-D TMA stores of [32 queries][128 B] (the store
-//                 clips tile columns / tile rows / queries outside the tensor); levels 1-3 are 2x2 means
-//                 formed in registers from the same accumulator values -- the patch is 8x8-aligned, so all
-//                 three pooled levels are patch-local; floor-mode dropping of odd rows/cols needs no code:
-//                 a level-k cell computed from a dropped row/col is itself outside H_k x W_k, i.e. tile
-//                 padding or a clipped tile.  Level 1 is TMA-stored, levels 2/3 (6% / 1.5% of the bytes)
-//                 are written with 32/8-byte global stores.
+//   main kernel   persistent, warp-specialised, 320 threads per CTA, one CTA per SM; template NCTA:
+//     NCTA = 1    (default) single-CTA MMAs, M = 128 queries x N = 128 targets.
+//     NCTA = 2    the two CTAs of a cluster pair up on ONE tcgen05.mma.cta_group::2 of M = 256 x N = 128: each CTA
+//                 keeps its own 128 query rows (A operand, accumulator) and supplies HALF of every B tile, so per
+//                 flop the pair moves half the B bytes through L2, the TMA unit and shared memory and the MMAs
+//                 issue at full rate (60 vs 83 cycles each).  Measured slower end to end (the epilogue's stores
+//                 bound the kernel and the pair couples two SMs' epilogues: 693 vs 643 us at cfg2), so it is
+//                 opt-in (RCB_TC_NCTA=2); both forms run the same parity tests.
+//     warp 0      TMA producer: B tiles (an 8 x 16 PATCH of target pixels x 64 channels; a 4-D box of the
+//                 [part*B, H, W, Kp] tensor, out-of-image rows/cols zero-filled; NCTA = 2: 4 patch rows per CTA)
+//                 stream through an mbarrier ring, two boxes per stage.
+//     warp 1      MMA issuer (the pair's leader CTA only): kind::f16, K = 16, the A operand comes from TENSOR MEMORY
+//                 (TS form), B through SWIZZLE_128B K-major smem descriptors, fp32 accumulators in TMEM.
+//     warps 2-9   epilogue, two warps per TMEM lane quarter (32 queries), split by output level: warps 2-5
+//                 tcgen05.ld the accumulator (lane = query, 64 columns = 4 patch rows x 16 targets = one band of
+//                 four 4x4 pyramid tiles = 256 contiguous bytes per query), scale by 1/sqrt(C) and send level 0
+//                 through SWIZZLE_128B staging boxes and 4-D TMA stores of [32 queries][128 B] (the store clips
+//                 tile columns / tile rows / queries outside the tensor).  Warps 6-9 read the same accumulator
+//                 and form levels 1-3 as 2x2 means in registers -- the patch is 8x8-aligned, so all three pooled
+//                 levels are patch-local; floor-mode dropping of odd rows/cols needs no code: a level-k cell
+//                 computed from a dropped row/col is itself outside H_k x W_k, i.e. tile padding or a clipped
+//                 tile.  Level 1 is TMA-stored, levels 2/3 (6% / 1.5% of the bytes) are written with 32/8-byte
+//                 global stores.  Warps 6-9 also place the A operand in tensor memory (global -> registers ->
+//                 tcgen05.st) at the start of every unit.
+//   work split    a unit = all patches of one (batch, query tile[s]); units go round-robin over the clusters, which
+//                 therefore sweep the same batch's patches in step (B tiles are found in L2); the units left over
+//                 after the full rounds are cut along the patch sequence so the last round is short, not idle.
+//   measured      (tools/time_build.py, tools/probe/tma_store_probe.cu, tools/power_probe.sh) the store path is the
+//                 bound: scattered 128-byte rows reach 3.5-5 TB/s through TMA stores, lane-scattered or octet-
+//                 coalesced st.global variants of the epilogue were slower, and in the 3-product mode the chip
+//                 sits at its 1 kW power cap (~1.55 GHz).
 #include <cstdlib>
 
 #include "rcb_common.cuh"
@@ -33,30 +48,25 @@ namespace rcb {
 
 namespace tc {
 
-constexpr int BM = 128;          // queries per tile (TMEM lanes)
+constexpr int BM = 128;          // queries per CTA tile (TMEM lanes)
 constexpr int PH = 8, PW = 16;   // target patch: 8 rows x 16 cols
 constexpr int BN = PH * PW;      // 128 targets per tile (TMEM columns)
 constexpr int BK = 64;           // bf16 channels per smem stage row (128 bytes, SWIZZLE_128B)
 constexpr int UMMA_K = 16;
 constexpr int MAX_KB = 4;        // Kp <= 256
-constexpr int MAX_STAGE = 12;    // B ring depth is chosen at launch from the shared memory left over by A
+constexpr int MAX_STAGE = 12;    // B ring depth is chosen at launch from the shared memory available
 constexpr int MAX_ACC = 4;       // TMEM accumulator buffers (128 columns each); count chosen at launch
-constexpr int A_TILE_BYTES = BM * BK * 2;  // 16 KB
-constexpr int B_TILE_BYTES = BN * BK * 2;  // 16 KB: one TMA box (128 targets x 64 channels)
+constexpr int B_TILE_BYTES = BN * BK * 2;  // 16 KB: one B box of the whole patch (half of it per CTA when NCTA = 2)
 constexpr int BOXES_PER_STAGE = 2;         // a ring stage = 2 boxes on one mbarrier: (kb,hi)+(kb,lo) or (kb)+(kb+1)
-constexpr int STAGE_BYTES = BOXES_PER_STAGE * B_TILE_BYTES;
 constexpr int STG_BYTES = 4096;            // one staged store box per warp
-constexpr int NUM_EPI_WARPS = 4;
-constexpr int THREADS = 32 * (2 + NUM_EPI_WARPS);      // A tiles in shared memory (SS MMA)
-constexpr int THREADS_TS = THREADS + 32 * 4;           // + 4 warps that place A in tensor memory (TS MMA)
+constexpr int NUM_EPI_WARPS = 4;           // per epilogue role (level 0 / pooled levels)
+constexpr int THREADS = 32 * (2 + 2 * NUM_EPI_WARPS);
 
 // Dynamic shared memory (all tile buffers 1024-byte aligned for the swizzle atoms):
-//   [0, a_bytes)            resident A tiles, index part * kblocks + kb
-//   [b_off, +nstage*16 KB)  B ring
-//   [stg_off, +32 KB)       epilogue staging, 2 x 4 KB per warp
-//   [bar_off, +1 KB)        mbarriers + TMEM base slot
+//   [b_off, +nstage * stage bytes)  B ring
+//   [stg_off, +8 * nstg * 4 KB)     epilogue staging rings, nstg boxes per warp
+//   [bar_off, +1 KB)                mbarriers + TMEM base slot
 constexpr int SMEM_BUDGET = 227 * 1024;
-constexpr int MAX_STG = 8;                 // staged store boxes per epilogue warp (ring; count chosen at launch)
 constexpr int BAR_BYTES = 1024;
 
 struct Params {
@@ -65,50 +75,110 @@ struct Params {
   int parts;        // 1 (bf16) or 2 (bf16x3)
   int levels;
   int mtiles;       // ceil(Q / 128)
+  int mgroups;      // ceil(mtiles / NCTA): query-tile groups, one tile per CTA of the cluster
   int pcols, prows; // patch grid
-  int groups;       // patch groups per (b, m-tile)
-  int patches_per_group;
-  int units;        // B * mtiles * groups
+  int npatch;       // pcols * prows
+  int full_rounds;  // rounds in which every cluster sweeps all patches of one (batch, query-tile group) unit
+  int tail_pieces, tail_split, tail_len;  // left-over units: cut into tail_split ranges of tail_len patches
   float scale;      // 1 / sqrt(C)
-  int direct_store; // debug: bypass the TMA stores
   int nstage, b_off, stg_off, bar_off;  // shared memory carve-up (bytes)
   int nstg;                             // staging boxes per epilogue warp
   int nacc, acc_col0;                   // TMEM: accumulator count, first accumulator column
   int Kp;                               // padded channel count
-  const uint32_t* a_pack;               // packed bf16 A operand, [part][B][Q][Kp/2] 32-bit words (TS kernel)
+  const uint32_t* a_pack;               // packed bf16 A operand, [part][B][Q][Kp/2] 32-bit words
   unsigned long long* prof;  // debug: per-CTA cycle counters (16 per CTA), null in production
-  int seq_chunks_per_cta;  // debug bit 1024
-  int debug_skip;   // debug bitmask: 1 skip L0 TMA store issue, 2 skip L1 store, 4 skip L2/L3, 8 skip staging writes
+  int debug_skip;   // debug bitmask: 1 skip L0 TMA store issue, 2 skip L1 store, 4 skip L2/L3, 8 skip staging writes,
+                    // 16 skip B loads, 32 skip MMAs, 64 skip TMEM loads, 128/256 plain arrives instead of commits
   float* pyr[RCB_MAX_LEVELS];
   int Hl[RCB_MAX_LEVELS], Wl[RCB_MAX_LEVELS], tx[RCB_MAX_LEVELS];  // level sizes, tiles per tile row
   long long ps[RCB_MAX_LEVELS];
 };
 
+// ---- cluster / tcgen05 PTX wrappers (NCTA = CTAs per MMA) -----------------------------------------
+RCB_DEVINL uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+RCB_DEVINL void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the mbarrier at the same shared-memory offset in CTA `cta` of the cluster (default semantics: a
+// cluster-scope release here costs ~1000 cycles per arrive and is not needed -- the data the barrier guards moves
+// through tensor memory / the async proxy, ordered by tcgen05.fence and the TMA complete_tx)
+RCB_DEVINL void mbar_arrive_cluster(uint32_t bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 r;\n\t"
+      "mapa.shared::cluster.u32 r, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [r];\n\t}"
+      ::"r"(bar), "r"(cta)
+      : "memory");
+}
+// 4-D TMA load of this CTA's part of a B tile; with NCTA = 2 the bytes are counted on the LEADER's mbarrier
+// (shared::cluster address of the same barrier in cluster rank 0: bit 24 of the address cleared)
+template <int NCTA>
+RCB_DEVINL void tma_load_b(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  if (NCTA == 1) {
+    tma_load_4d(dst, map, bar, c0, c1, c2, c3);
+  } else {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+  }
+}
+template <int NCTA>
 RCB_DEVINL void tmem_alloc(uint32_t slot_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(ncols)
-               : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  if (NCTA == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  } else {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
 }
+template <int NCTA>
 RCB_DEVINL void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+  if (NCTA == 1)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+  else
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
-// D[tmem] (+)= A[smem] * B[smem]^T, bf16 operands, fp32 accumulate
-RCB_DEVINL void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// same with the A operand in tensor memory (lane = row, one 32-bit column = two consecutive bf16 of K)
+// D[tmem] (+)= A[tmem] * B[smem]^T, bf16 operands, fp32 accumulate; A: lane = row, one 32-bit column = two
+// consecutive bf16 of K.  NCTA = 2: issued by the leader for the pair, every address is the same offset in both CTAs.
+template <int NCTA>
 RCB_DEVINL void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
+  if (NCTA == 1) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+// mbarrier arrives when all previously issued tcgen05.mma of this thread have completed; NCTA = 2: on the barrier
+// at this offset in BOTH CTAs of the pair
+template <int NCTA>
+RCB_DEVINL void umma_commit(uint32_t bar) {
+  if (NCTA == 1) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+  } else {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)3)
+                 : "memory");
+  }
 }
 // registers -> tensor memory: lane i of the warp writes 32 consecutive 32-bit columns of TMEM lane (base + i)
 RCB_DEVINL void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
@@ -123,10 +193,6 @@ RCB_DEVINL void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
       : "memory");
 }
 RCB_DEVINL void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-// mbarrier arrives when all previously issued tcgen05.mma of this thread have completed
-RCB_DEVINL void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
 RCB_DEVINL void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   uint32_t r[32];
   asm volatile(
@@ -154,10 +220,10 @@ RCB_DEVINL uint64_t make_smem_desc(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;                      // SWIZZLE_128B
   return d;
 }
-// kind::f16 instruction descriptor: fp32 accumulate, bf16 x bf16, both K-major, M=128, N=128
-__host__ __device__ constexpr uint32_t make_idesc() {
+// kind::f16 instruction descriptor: fp32 accumulate, bf16 x bf16, both K-major, M = 128 * NCTA, N = 128
+__host__ __device__ constexpr uint32_t make_idesc(int ncta) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(BN >> 3) << 17) |
-         ((uint32_t)(BM >> 4) << 24);
+         ((uint32_t)((BM * ncta) >> 4) << 24);
 }
 
 // ---- operand packing -----------------------------------------------------------------------
@@ -197,35 +263,26 @@ pack_operands_kernel(const float* __restrict__ f1, const float* __restrict__ f2,
 }
 
 // ---- main kernel -------------------------------------------------------------------------------
-struct UnitCoord {
+// One piece of a cluster's work: a patch range of one (batch, query tile) unit.
+struct Segment {
   int b, mt, p_begin, p_end;
 };
-RCB_DEVINL UnitCoord decode_unit(const Params& p, int u) {
-  UnitCoord c;
-  const int g = u % p.groups;
-  const int t = u / p.groups;
-  c.mt = t % p.mtiles;
-  c.b = t / p.mtiles;
-  const int npatch = p.pcols * p.prows;
-  c.p_begin = g * p.patches_per_group;
-  c.p_end = min(npatch, c.p_begin + p.patches_per_group);
-  return c;
-}
 
-// TS = false: A tiles resident in shared memory (SS MMA), 192 threads.
-// TS = true : A resident in tensor memory (TS MMA), written there by 4 extra warps; the MMA then reads only B from
-//             shared memory, which halves its shared-memory traffic (the kernel is shared-memory-bandwidth bound:
-//             an M=128,N=128 SS MMA alone consumes the full 128 B/clk) and frees 128 KB for a deeper B ring.
-template <bool TS>
-__global__ void __launch_bounds__(TS ? THREADS_TS : THREADS, 1)
-build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                const __grid_constant__ CUtensorMap map_l0, const __grid_constant__ CUtensorMap map_l1,
-                const __grid_constant__ CUtensorMap map_seq, const Params p) {
+template <int NCTA>
+__global__ void __launch_bounds__(THREADS, 1)
+build_tc_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_l0,
+                const __grid_constant__ CUtensorMap map_l1, const Params p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const uint32_t smem_base = smem_u32(smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t crank = NCTA == 2 ? cluster_ctarank() : 0u;  // rank inside the MMA pair; rank 0 leads
+  const bool leader = crank == 0;
+  constexpr int STAGE_BYTES = BOXES_PER_STAGE * B_TILE_BYTES / NCTA;  // per CTA
+  constexpr int BOX_BYTES = B_TILE_BYTES / NCTA;
 
-  // barriers (8 bytes each)
+  // barriers (8 bytes each).  With NCTA = 2 the barriers the MMA issuer waits on (a_full, b_full, acc_empty) are
+  // the LEADER's copies and collect arrivals from both CTAs; the ones it signals (a_empty, b_empty, acc_full)
+  // exist in both CTAs and are signalled by one multicast commit.
   const uint32_t bar0 = smem_base + p.bar_off;
   const int NSTAGE = p.nstage;
   const uint32_t a_full = bar0, a_empty = bar0 + 8;
@@ -239,47 +296,58 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       reinterpret_cast<volatile uint32_t*>(smem + p.bar_off + 16 + 16 * MAX_STAGE + 16 * MAX_ACC);
 
   if (threadIdx.x == 0) {
-    mbar_init(a_full, TS ? 4 : 1);  // TS: one arrival per A-loader warp; SS: the producer's expect_tx
+    mbar_init(a_full, NUM_EPI_WARPS * NCTA);  // the pooled-levels warps of every CTA of the pair load A
     mbar_init(a_empty, 1);
     for (int s = 0; s < NSTAGE; ++s) {
-      mbar_init(b_full(s), 1);
+      mbar_init(b_full(s), 1);  // the leader's producer arrives with the byte count of BOTH CTAs' boxes
       mbar_init(b_empty(s), 1);
     }
     for (int s = 0; s < NACC; ++s) {
       mbar_init(acc_full(s), 1);
-      mbar_init(acc_empty(s), NUM_EPI_WARPS);
+      mbar_init(acc_empty(s), 2 * NUM_EPI_WARPS * NCTA);
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  if (warp == 1) tmem_alloc<NCTA>(tmem_slot, 512);
   tc_fence_before();
-  __syncthreads();
+  if (NCTA == 2) cluster_sync_all();
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+
+  // This cluster's work: segment i < full_rounds is the whole patch sweep of unit i * nclus + cid (unit = batch,
+  // query-tile group); the units left over after the full rounds are cut into `tail_split` patch ranges each so that
+  // every cluster gets at most one piece.  Clusters of one round sweep the same batch's patches in step, so a B tile
+  // is fetched from DRAM once and found in L2 by the other clusters.
+  const int nclus = gridDim.x / NCTA, cid = blockIdx.x / NCTA;
+  const int nseg = p.full_rounds + (cid < p.tail_pieces ? 1 : 0);
+  auto segment = [&](int i) {
+    Segment sg;
+    int u;
+    if (i < p.full_rounds) {
+      u = i * nclus + cid;
+      sg.p_begin = 0;
+      sg.p_end = p.npatch;
+    } else {
+      u = p.full_rounds * nclus + cid / p.tail_split;
+      sg.p_begin = (cid % p.tail_split) * p.tail_len;
+      sg.p_end = min(p.npatch, sg.p_begin + p.tail_len);
+    }
+    sg.b = u / p.mgroups;
+    sg.mt = (u % p.mgroups) * NCTA + (int)crank;  // may be >= mtiles for the pair's second CTA: all-padding tile
+    return sg;
+  };
 
   if (warp == 0) {
     // =============================== TMA producer (whole warp runs the loop, one elected lane issues) ====
     int s = 0;           // B ring slot
     uint32_t ph = 0;     // its phase
-    uint32_t nunit = 0;
-    long long w_b = 0, w_a = 0;
+    long long w_b = 0;
     long long* pw_b = p.prof ? &w_b : nullptr;
-    long long* pw_a = p.prof ? &w_a : nullptr;
-    const long long t_begin = clock64();
-    for (int u = blockIdx.x; u < p.units; u += gridDim.x, ++nunit) {
-      const UnitCoord uc = decode_unit(p, u);
-      if (!TS) {
-        if (nunit > 0) mbar_wait_t(a_empty, (nunit - 1) & 1, pw_a);  // previous unit's MMAs have drained A
-        if (elect_one()) {
-          mbar_expect_tx(a_full, (uint32_t)(p.parts * p.kblocks * A_TILE_BYTES));
-          for (int part = 0; part < p.parts; ++part)
-            for (int kb = 0; kb < p.kblocks; ++kb)
-              tma_load_3d(smem_base + (part * p.kblocks + kb) * A_TILE_BYTES, &map_a, a_full, kb * BK, uc.mt * BM,
-                          part * p.B + uc.b);
-        }
-        __syncwarp();
-      }
-      for (int pi = uc.p_begin; pi < uc.p_end; ++pi) {
+    const long long clk0 = clock64();
+    for (int si = 0; si < nseg; ++si) {
+      const Segment sg = segment(si);
+      for (int pi = sg.p_begin; pi < sg.p_end; ++pi) {
         const int py = pi / p.pcols, px = pi % p.pcols;
         const int nb = p.kblocks * p.parts;  // boxes of this tile in (kb, part) order
         for (int j = 0; j < nb; j += BOXES_PER_STAGE) {
@@ -287,14 +355,16 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           if (elect_one()) {
             const int nbox = min(BOXES_PER_STAGE, nb - j);
             if (p.debug_skip & 16) {
-              mbar_arrive(b_full(s));
+              if (leader) mbar_arrive(b_full(s));
             } else {
-              mbar_expect_tx(b_full(s), (uint32_t)(nbox * B_TILE_BYTES));
-              for (int t = 0; t < nbox; ++t) {
-                const int jj = j + t;
+              // The peer's boxes are counted on the leader's barrier too; it cannot run a ring lap ahead because
+              // its b_empty is only signalled after the leader's MMAs consumed this phase.
+              if (leader) mbar_expect_tx(b_full(s), (uint32_t)(nbox * B_TILE_BYTES));
+              for (int i = 0; i < nbox; ++i) {
+                const int jj = j + i;
                 const int kb = p.parts == 2 ? jj >> 1 : jj, part = p.parts == 2 ? jj & 1 : 0;
-                tma_load_4d(smem_base + p.b_off + s * STAGE_BYTES + t * B_TILE_BYTES, &map_b, b_full(s), kb * BK, px * PW,
-                            py * PH, part * p.B + uc.b);
+                tma_load_b<NCTA>(smem_base + p.b_off + s * STAGE_BYTES + i * BOX_BYTES, &map_b, b_full(s), kb * BK,
+                                 px * PW, py * PH + (int)crank * (PH / NCTA), part * p.B + sg.b);
               }
             }
           }
@@ -304,94 +374,105 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       }
     }
     if (p.prof && lane == 0) {
-      p.prof[blockIdx.x * 16 + 0] = clock64() - t_begin;
+      p.prof[blockIdx.x * 16 + 0] = clock64() - clk0;
       p.prof[blockIdx.x * 16 + 1] = w_b;
-      p.prof[blockIdx.x * 16 + 2] = w_a;
+      p.prof[blockIdx.x * 16 + 2] = 0;
     }
   } else if (warp == 1) {
-    // =============================== MMA issuer (whole warp runs the loop, one elected lane issues) ======
-    constexpr uint32_t idesc = make_idesc();
-    const uint64_t desc_base = make_smem_desc(0);  // everything but the start address
-    int s = 0, buf = 0;
-    uint32_t ph = 0, aph = 0, tile = 0, nunit = 0;
-    long long w_bf = 0, w_acc = 0, w_af = 0;
-    long long* pw_bf = p.prof ? &w_bf : nullptr;
-    long long* pw_acc = p.prof ? &w_acc : nullptr;
-    long long* pw_af = p.prof ? &w_af : nullptr;
-    const long long t_begin = clock64();
-    for (int u = blockIdx.x; u < p.units; u += gridDim.x, ++nunit) {
-      const UnitCoord uc = decode_unit(p, u);
-      mbar_wait_t(a_full, nunit & 1, pw_af);
-      tc_fence_after();
-      for (int pi = uc.p_begin; pi < uc.p_end; ++pi, ++tile) {
-        mbar_wait_t(acc_empty(buf), aph ^ 1, pw_acc);
+    // =============================== MMA issuer (leader CTA; whole warp runs the loop, one lane issues) ===
+    if (leader) {
+      constexpr uint32_t idesc = make_idesc(NCTA);
+      const uint64_t desc_base = make_smem_desc(0);  // everything but the start address
+      int s = 0, buf = 0;
+      uint32_t ph = 0, aph = 0, nunit = 0;
+      long long w_bf = 0, w_acc = 0, w_af = 0;
+      long long* pw_bf = p.prof ? &w_bf : nullptr;
+      long long* pw_acc = p.prof ? &w_acc : nullptr;
+      long long* pw_af = p.prof ? &w_af : nullptr;
+      const long long clk0 = clock64();
+      for (int si = 0; si < nseg; ++si, ++nunit) {
+        const Segment sg = segment(si);
+        mbar_wait_t(a_full, nunit & 1, pw_af);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + p.acc_col0 + buf * BN;
-        uint32_t acc = 0;
-        const int nb = p.kblocks * p.parts;
-        for (int j = 0; j < nb; j += BOXES_PER_STAGE) {
-          mbar_wait_t(b_full(s), ph, pw_bf);
+        for (int pi = sg.p_begin; pi < sg.p_end; ++pi) {
+          mbar_wait_t(acc_empty(buf), aph ^ 1, pw_acc);
           tc_fence_after();
-          if (elect_one()) {
-            const int nbox = min(BOXES_PER_STAGE, nb - j);
-            if (!(p.debug_skip & 32)) {
-              for (int t = 0; t < nbox; ++t) {
-                const int jj = j + t;
-                const int kb = p.parts == 2 ? jj >> 1 : jj, part = p.parts == 2 ? jj & 1 : 0;
-                const uint64_t bdesc =
-                    desc_base | (uint64_t)(((smem_base + p.b_off + s * STAGE_BYTES + t * B_TILE_BYTES) >> 4) & 0x3FFF);
-                const uint32_t ta_hi = tmem_base + kb * (BK / 2);  // TS: A columns of this k-block
-                const uint32_t ta_lo = tmem_base + (p.Kp >> 1) + kb * (BK / 2);
-                const uint64_t a_hi = desc_base | (uint64_t)(((smem_base + kb * A_TILE_BYTES) >> 4) & 0x3FFF);
-                const uint64_t a_lo = desc_base | (uint64_t)(((smem_base + (p.kblocks + kb) * A_TILE_BYTES) >> 4) & 0x3FFF);
+          const uint32_t d_tmem = tmem_base + p.acc_col0 + buf * BN;
+          uint32_t acc = 0;
+          const int nb = p.kblocks * p.parts;
+          for (int j = 0; j < nb; j += BOXES_PER_STAGE) {
+            mbar_wait_t(b_full(s), ph, pw_bf);
+            tc_fence_after();
+            if (elect_one()) {
+              const int nbox = min(BOXES_PER_STAGE, nb - j);
+              if (!(p.debug_skip & 32)) {
+                for (int i = 0; i < nbox; ++i) {
+                  const int jj = j + i;
+                  const int kb = p.parts == 2 ? jj >> 1 : jj, part = p.parts == 2 ? jj & 1 : 0;
+                  const uint64_t bdesc =
+                      desc_base | (uint64_t)(((smem_base + p.b_off + s * STAGE_BYTES + i * BOX_BYTES) >> 4) & 0x3FFF);
+                  const uint32_t ta_hi = tmem_base + kb * (BK / 2);  // A columns of this k-block
+                  const uint32_t ta_lo = tmem_base + (p.Kp >> 1) + kb * (BK / 2);
 #pragma unroll
-                for (int k = 0; k < BK / UMMA_K; ++k) {  // +32 bytes (smem) / +8 columns (TMEM) per K step
-                  if (TS) umma_bf16_ts(d_tmem, ta_hi + 8 * k, bdesc + 2 * k, idesc, acc);
-                  else umma_bf16(d_tmem, a_hi + 2 * k, bdesc + 2 * k, idesc, acc);
-                  acc = 1;
-                }
-                if (part == 0 && p.parts > 1) {  // B_hi also meets A_lo
+                  for (int k = 0; k < BK / UMMA_K; ++k) {  // +32 bytes (smem) / +8 columns (TMEM) per K step
+                    umma_bf16_ts<NCTA>(d_tmem, ta_hi + 8 * k, bdesc + 2 * k, idesc, acc);
+                    acc = 1;
+                  }
+                  if (part == 0 && p.parts > 1) {  // B_hi also meets A_lo
 #pragma unroll
-                  for (int k = 0; k < BK / UMMA_K; ++k) {
-                    if (TS) umma_bf16_ts(d_tmem, ta_lo + 8 * k, bdesc + 2 * k, idesc, 1u);
-                    else umma_bf16(d_tmem, a_lo + 2 * k, bdesc + 2 * k, idesc, 1u);
+                    for (int k = 0; k < BK / UMMA_K; ++k)
+                      umma_bf16_ts<NCTA>(d_tmem, ta_lo + 8 * k, bdesc + 2 * k, idesc, 1u);
                   }
                 }
               }
+              if (p.debug_skip & 128) {
+                mbar_arrive(b_empty(s));
+                if (NCTA == 2) mbar_arrive_cluster(b_empty(s), 1);
+              } else {
+                umma_commit<NCTA>(b_empty(s));  // frees the stage (in both CTAs) once these MMAs have read it
+              }
             }
-            if (p.debug_skip & 128) mbar_arrive(b_empty(s));
-            else umma_commit(b_empty(s));  // frees the stage once these MMAs have read it
+            acc = 1;
+            __syncwarp();
+            if (++s == NSTAGE) { s = 0; ph ^= 1; }
           }
-          acc = 1;
+          if (elect_one()) {
+            if (p.debug_skip & 256) {
+              mbar_arrive(acc_full(buf));
+              if (NCTA == 2) mbar_arrive_cluster(acc_full(buf), 1);
+            } else {
+              umma_commit<NCTA>(acc_full(buf));
+            }
+          }
           __syncwarp();
-          if (++s == NSTAGE) { s = 0; ph ^= 1; }
+          if (++buf == NACC) { buf = 0; aph ^= 1; }
         }
-        if (elect_one()) {
-          if (p.debug_skip & 256) mbar_arrive(acc_full(buf));
-          else umma_commit(acc_full(buf));
-        }
+        if (elect_one()) umma_commit<NCTA>(a_empty);
         __syncwarp();
-        if (++buf == NACC) { buf = 0; aph ^= 1; }
       }
-      if (elect_one()) umma_commit(a_empty);
-      __syncwarp();
+      if (p.prof && lane == 0) {
+        p.prof[blockIdx.x * 16 + 3] = clock64() - clk0;
+        p.prof[blockIdx.x * 16 + 4] = w_bf;
+        p.prof[blockIdx.x * 16 + 5] = w_acc;
+        p.prof[blockIdx.x * 16 + 6] = w_af;
+      }
     }
-    if (p.prof && lane == 0) {
-      p.prof[blockIdx.x * 16 + 3] = clock64() - t_begin;
-      p.prof[blockIdx.x * 16 + 4] = w_bf;
-      p.prof[blockIdx.x * 16 + 5] = w_acc;
-      p.prof[blockIdx.x * 16 + 6] = w_af;
-    }
-  } else if (warp < 2 + NUM_EPI_WARPS) {
-    // =============================== epilogue ===============================
-    const int ew = warp - 2;             // staging slot
+  } else {
+    // =============================== epilogue (+ A loading) ===============================
+    // Two warps per TMEM lane quarter (warp w works on quarter w % 4 = 32 queries), split by OUTPUT LEVEL so that
+    // every global write keeps its full width (128-byte rows; 64-byte rows and 8-byte stores measured 2-4x more
+    // expensive per byte):
+    //   warps 2-5  level 0: tcgen05.ld, scale, four staged boxes [32 queries][2 tiles = 128 B] per tile
+    //   warps 6-9  levels 1-3: tcgen05.ld, scale, 2x2 means in registers, one staged level-1 box and the few
+    //              level-2/3 values; they also place the A operand in tensor memory at the start of every unit.
+    const bool pooled_role = warp >= 2 + NUM_EPI_WARPS;
+    const int ew = warp - 2;             // staging ring slot
+    const int lane_q = (warp & 3) * 32;  // TMEM lane quarter this warp may access
     int buf = 0;
     uint32_t aph = 0;
-    const int lane_q = (warp & 3) * 32;  // TMEM lane quarter this warp may access
     const int NSTG = p.nstg;
     unsigned char* stg = smem + p.stg_off + ew * NSTG * STG_BYTES;
-    uint32_t nstore = 0;  // staged stores issued by this warp
-    int sbuf = 0;         // staging ring position = nstore % NSTG
+    int sbuf = 0;  // staging ring position
     // the bulk group that last used a staging buffer is NSTG groups old: wait until at most NSTG - 1 are unread
     auto wait_stg = [&]() {
       if (lane == 0) {
@@ -399,223 +480,217 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           case 2: tma_store_wait_read<1>(); break;
           case 3: tma_store_wait_read<2>(); break;
           case 4: tma_store_wait_read<3>(); break;
-          case 6: tma_store_wait_read<5>(); break;
-          default: tma_store_wait_read<7>(); break;
+          default: tma_store_wait_read<5>(); break;
         }
       }
       __syncwarp();
     };
-    uint32_t tile = 0;
+    auto release_acc = [&]() {  // all TMEM reads of this accumulator are done: hand it back to the MMA issuer
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (NCTA == 1) mbar_arrive(acc_empty(buf));
+        else mbar_arrive_cluster(acc_empty(buf), 0);
+      }
+      if (++buf == NACC) { buf = 0; aph ^= 1; }
+    };
+    const int words = p.Kp >> 1;  // 32-bit words per packed A row and part (multiple of 32)
+    uint32_t tile = 0, nunit = 0;
     long long w_full = 0, w_st = 0, w_ld = 0;
     long long* pw_full = p.prof ? &w_full : nullptr;
-    const long long t_begin = clock64();
-    for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
-      const UnitCoord uc = decode_unit(p, u);
-      const int q_w = uc.mt * BM + lane_q;  // first query of this warp
+    const long long clk0 = clock64();
+    for (int si = 0; si < nseg; ++si, ++nunit) {
+      const Segment sg = segment(si);
+      const int q_w = sg.mt * BM + lane_q;  // first query of this warp
       const int q = q_w + lane;
       const bool q_ok = q < p.Q;
-      const long long bq = (long long)uc.b * p.Q + q;
-      for (int pi = uc.p_begin; pi < uc.p_end; ++pi, ++tile) {
+      const long long bq = (long long)sg.b * p.Q + q;
+      if (pooled_role) {
+        // ---- A operand of this unit: global -> registers -> tensor memory.  Lane i copies the packed bf16 row of
+        // its query (Kp/2 32-bit words per part) into columns [part*Kp/2, ...) of its TMEM lane.
+        for (int part = 0; part < p.parts; ++part) {
+          // all loads of a part are in flight before the first store (128 registers at Kp = 256); the loads of
+          // part 0 are issued before waiting for the previous unit to release A
+          const uint4* row = reinterpret_cast<const uint4*>(
+              p.a_pack + (((long long)part * p.B + sg.b) * p.Q + (q_ok ? q : 0)) * words);
+          uint32_t r[MAX_KB][32];
+#pragma unroll
+          for (int ch = 0; ch < MAX_KB; ++ch) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              uint4 v = make_uint4(0u, 0u, 0u, 0u);
+              if (q_ok && ch * 32 < words) v = __ldg(row + ch * 8 + i);
+              r[ch][4 * i + 0] = v.x; r[ch][4 * i + 1] = v.y; r[ch][4 * i + 2] = v.z; r[ch][4 * i + 3] = v.w;
+            }
+          }
+          if (part == 0 && nunit > 0) mbar_wait(a_empty, (nunit - 1) & 1);  // previous unit's MMAs are done with A
+          if (part == 0) tc_fence_after();
+#pragma unroll
+          for (int ch = 0; ch < MAX_KB; ++ch)
+            if (ch * 32 < words) tmem_st32(tmem_base + ((uint32_t)lane_q << 16) + part * words + ch * 32, r[ch]);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (NCTA == 1) mbar_arrive(a_full);
+          else mbar_arrive_cluster(a_full, 0);
+        }
+      }
+      for (int pi = sg.p_begin; pi < sg.p_end; ++pi, ++tile) {
         const int py = pi / p.pcols, px = pi % p.pcols;
         const int y0 = py * PH, x0 = px * PW;
         mbar_wait_t(acc_full(buf), aph, pw_full);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)lane_q << 16) + p.acc_col0 + buf * BN;
-        float l1[4][8];
+        if (!pooled_role) {
+          // ---------------- level 0 ----------------
 #pragma unroll
-        for (int band = 0; band < 2; ++band) {  // 4 patch rows = one row of 4x4 tiles
-          float va[32], vb[32];                 // rows 4*band + {0,1} and + {2,3}, 16 columns each
-          if (p.debug_skip & 64) {
+          for (int band = 0; band < 2; ++band) {  // 4 patch rows = one row of 4x4 tiles
+            float va[32], vb[32];                 // rows 4*band + {0,1} and + {2,3}, 16 columns each
+            if (p.debug_skip & 64) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) va[i] = vb[i] = 0.f;
-          } else {
-            const long long t0 = p.prof ? clock64() : 0;
-            tmem_ld32(taddr + band * 64, va);
-            tmem_ld32(taddr + band * 64 + 32, vb);
-            if (p.prof) w_ld += clock64() - t0;
-          }
+              for (int i = 0; i < 32; ++i) va[i] = vb[i] = 0.f;
+            } else {
+              const long long c0 = p.prof ? clock64() : 0;
+              tmem_ld32(taddr + band * 64, va);
+              tmem_ld32(taddr + band * 64 + 32, vb);
+              if (p.prof) w_ld += clock64() - c0;
+            }
+            if (band == 1) release_acc();  // both bands are in registers
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            va[i] *= p.scale;
-            vb[i] *= p.scale;
-          }
+            for (int i = 0; i < 32; ++i) {
+              va[i] *= p.scale;
+              vb[i] *= p.scale;
+            }
+            const int yy = y0 + 4 * band;
+            if (yy < p.H && q_w < p.Q) {  // warp-uniform
+              // The band's 4 tiles are 256 contiguous bytes per query; they leave as two 128-byte halves
+              // (2 tiles each) through a SWIZZLE_128B staging box [32 queries][128 B]: conflict-free st.shared.
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            l1[2 * band][j] = ((va[2 * j] + va[2 * j + 1]) + (va[16 + 2 * j] + va[16 + 2 * j + 1])) * 0.25f;
-            l1[2 * band + 1][j] = ((vb[2 * j] + vb[2 * j + 1]) + (vb[16 + 2 * j] + vb[16 + 2 * j + 1])) * 0.25f;
-          }
-          const int yy = y0 + 4 * band;
-          if (p.direct_store) {
-            if (q_ok) {
-              float* plane = p.pyr[0] + bq * p.ps[0];
-#pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                const int x = x0 + (i & 15);
-                if (x < p.W) {
-                  if (yy + (i >> 4) < p.H) plane[tile_off(yy + (i >> 4), x, p.tx[0])] = va[i];
-                  if (yy + 2 + (i >> 4) < p.H) plane[tile_off(yy + 2 + (i >> 4), x, p.tx[0])] = vb[i];
+              for (int half = 0; half < 2; ++half) {
+                if (x0 + 8 * half >= p.W) break;  // warp-uniform: these tiles do not exist
+                unsigned char* sb = stg + sbuf * STG_BYTES;
+                {
+                  const long long c0 = p.prof ? clock64() : 0;
+                  wait_stg();  // the store that used this buffer has been read out
+                  if (p.prof) w_st += clock64() - c0;
                 }
+                if (!(p.debug_skip & 8)) {
+#pragma unroll
+                  for (int c = 0; c < 8; ++c) {  // chunk c = tile (c >> 2) of this half, tile row (c & 3)
+                    const int col = 8 * half + 4 * (c >> 2);
+                    const int r = c & 3;
+                    const float* src = (r < 2) ? va : vb;
+                    const int o = (r & 1) * 16 + col;
+                    *reinterpret_cast<float4*>(sb + lane * 128 + ((c ^ (lane & 7)) << 4)) =
+                        make_float4(src[o], src[o + 1], src[o + 2], src[o + 3]);
+                  }
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0 && !(p.debug_skip & 1)) {
+                  tma_store_4d(&map_l0, smem_u32(sb), ((x0 >> 2) + 2 * half) * 16, (yy >> 2), q_w, sg.b);
+                  tma_store_commit();
+                }
+                if (++sbuf == NSTG) sbuf = 0;
               }
             }
-          } else if (yy < p.H && q_w < p.Q) {  // warp-uniform
-            // The band's 4 tiles are 256 contiguous bytes per query; they leave as two 128-byte halves
-            // (2 tiles each) through a SWIZZLE_128B staging box [32 queries][128 B]: conflict-free st.shared.
+          }
+        } else {
+          // ---------------- levels 1-3: 2x2 means of the same accumulator values ----------------
+          float l1[4][8];
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-              if (x0 + 8 * half >= p.W) break;  // warp-uniform: these tiles do not exist
+          for (int band = 0; band < 2; ++band) {
+            float va[32], vb[32];
+            if (p.debug_skip & 64) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) va[i] = vb[i] = 0.f;
+            } else {
+              tmem_ld32(taddr + band * 64, va);
+              tmem_ld32(taddr + band * 64 + 32, vb);
+            }
+            // scaled first: level 1 is the mean of the STORED level-0 values, bit for bit
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              va[i] *= p.scale;
+              vb[i] *= p.scale;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              l1[2 * band][j] = ((va[2 * j] + va[2 * j + 1]) + (va[16 + 2 * j] + va[16 + 2 * j + 1])) * 0.25f;
+              l1[2 * band + 1][j] = ((vb[2 * j] + vb[2 * j + 1]) + (vb[16 + 2 * j] + vb[16 + 2 * j + 1])) * 0.25f;
+            }
+          }
+          release_acc();
+          if (p.levels > 1) {
+            const int y1 = y0 >> 1, x1 = x0 >> 1;  // 4 rows x 8 cols = 2 tiles = 128 contiguous bytes per query
+            if (y1 < p.Hl[1] && x1 < p.Wl[1] && q_w < p.Q && !(p.debug_skip & 2)) {
               unsigned char* sb = stg + sbuf * STG_BYTES;
-              {
-                const long long t0 = p.prof ? clock64() : 0;
-                wait_stg();  // the store that used this buffer has been read out
-                if (p.prof) w_st += clock64() - t0;
-              }
-              if (!(p.debug_skip & 8)) {
+              wait_stg();
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {  // chunk c = tile (c >> 2) of this half, tile row (c & 3)
-                  const int col = 8 * half + 4 * (c >> 2);
-                  const int r = c & 3;
-                  const float* src = (r < 2) ? va : vb;
-                  const int o = (r & 1) * 16 + col;
-                  *reinterpret_cast<float4*>(sb + lane * 128 + ((c ^ (lane & 7)) << 4)) =
-                      make_float4(src[o], src[o + 1], src[o + 2], src[o + 3]);
-                }
+              for (int c = 0; c < 8; ++c) {  // chunk c = tile (c >> 2), tile row (c & 3)
+                const int r = c & 3, col = 4 * (c >> 2);
+                *reinterpret_cast<float4*>(sb + lane * 128 + ((c ^ (lane & 7)) << 4)) =
+                    make_float4(l1[r][col], l1[r][col + 1], l1[r][col + 2], l1[r][col + 3]);
               }
               fence_proxy_async_smem();
               __syncwarp();
-              if (lane == 0 && !(p.debug_skip & 1)) {
-                // debug bit 512: alias all queries onto 128 planes so the stores stay L2-resident (no DRAM writes)
-                // debug bit 1024: write the boxes as consecutive 4 KB chunks (sequential DRAM pattern, wrong layout)
-                if (p.debug_skip & 1024)
-                  tma_store_2d(&map_seq, smem_u32(sb), 0,
-                               (int)(((long long)blockIdx.x * p.seq_chunks_per_cta + (nstore * NUM_EPI_WARPS + ew) % p.seq_chunks_per_cta) * 32));
-                else
-                  tma_store_4d(&map_l0, smem_u32(sb), ((x0 >> 2) + 2 * half) * 16, (yy >> 2),
-                               (p.debug_skip & 512) ? (q_w & 127) : q_w, (p.debug_skip & 512) ? 0 : uc.b);
+              if (lane == 0) {
+                tma_store_4d(&map_l1, smem_u32(sb), (x1 >> 2) * 16, (y1 >> 2), q_w, sg.b);
                 tma_store_commit();
               }
-              ++nstore;
               if (++sbuf == NSTG) sbuf = 0;
             }
           }
-        }
-        // all TMEM reads of this accumulator are done: hand it back to the MMA warp
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(acc_empty(buf));
-        const int buf_done = buf;
-        (void)buf_done;
-        if (++buf == NACC) { buf = 0; aph ^= 1; }
-
-        if (p.levels > 1) {
-          const int y1 = y0 >> 1, x1 = x0 >> 1;  // 4 rows x 8 cols = 2 tiles = 128 contiguous bytes per query
-          if (p.direct_store) {
-            if (q_ok) {
-              float* plane = p.pyr[1] + bq * p.ps[1];
+          if (p.levels > 2 && q_ok && !(p.debug_skip & 4)) {
+            float l2[2][4];
 #pragma unroll
-              for (int r = 0; r < 4; ++r)
+            for (int r = 0; r < 2; ++r)
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
-                  if (y1 + r < p.Hl[1] && x1 + j < p.Wl[1]) plane[tile_off(y1 + r, x1 + j, p.tx[1])] = l1[r][j];
+              for (int j = 0; j < 4; ++j)
+                l2[r][j] = ((l1[2 * r][2 * j] + l1[2 * r][2 * j + 1]) + (l1[2 * r + 1][2 * j] + l1[2 * r + 1][2 * j + 1])) * 0.25f;
+            // level 2: 2 rows x 4 cols = two adjacent 16-byte rows of one tile (y2 is even, x2 a multiple of 4)
+            const int y2 = y0 >> 2, x2 = x0 >> 2;
+            if (y2 < p.Hl[2] && x2 < p.Wl[2]) {
+              float* t2 = p.pyr[2] + bq * p.ps[2] + tile_off(y2, x2, p.tx[2]);
+              *reinterpret_cast<float4*>(t2) = make_float4(l2[0][0], l2[0][1], l2[0][2], l2[0][3]);
+              *reinterpret_cast<float4*>(t2 + 4) = make_float4(l2[1][0], l2[1][1], l2[1][2], l2[1][3]);
             }
-          } else if (y1 < p.Hl[1] && x1 < p.Wl[1] && q_w < p.Q && !(p.debug_skip & 2)) {
-            unsigned char* sb = stg + sbuf * STG_BYTES;
-            wait_stg();
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {  // chunk c = tile (c >> 2), tile row (c & 3)
-              const int r = c & 3, col = 4 * (c >> 2);
-              *reinterpret_cast<float4*>(sb + lane * 128 + ((c ^ (lane & 7)) << 4)) =
-                  make_float4(l1[r][col], l1[r][col + 1], l1[r][col + 2], l1[r][col + 3]);
+            if (p.levels > 3) {
+              const float a = ((l2[0][0] + l2[0][1]) + (l2[1][0] + l2[1][1])) * 0.25f;
+              const float c = ((l2[0][2] + l2[0][3]) + (l2[1][2] + l2[1][3])) * 0.25f;
+              const int y3 = y0 >> 3, x3 = x0 >> 3;  // x3 is even: both values sit in one tile row
+              if (y3 < p.Hl[3] && x3 < p.Wl[3])
+                *reinterpret_cast<float2*>(p.pyr[3] + bq * p.ps[3] + tile_off(y3, x3, p.tx[3])) = make_float2(a, c);
             }
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) {
-              tma_store_4d(&map_l1, smem_u32(sb), (x1 >> 2) * 16, (y1 >> 2), q_w, uc.b);
-              tma_store_commit();
-            }
-            ++nstore;
-            if (++sbuf == NSTG) sbuf = 0;
-          }
-        }
-        if (p.levels > 2 && q_ok && !(p.debug_skip & 4)) {
-          float l2[2][4];
-#pragma unroll
-          for (int r = 0; r < 2; ++r)
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              l2[r][j] = ((l1[2 * r][2 * j] + l1[2 * r][2 * j + 1]) + (l1[2 * r + 1][2 * j] + l1[2 * r + 1][2 * j + 1])) * 0.25f;
-          // level 2: 2 rows x 4 cols = two adjacent 16-byte rows of one tile (y2 is even, x2 a multiple of 4)
-          const int y2 = y0 >> 2, x2 = x0 >> 2;
-          if (y2 < p.Hl[2] && x2 < p.Wl[2]) {
-            float* t2 = p.pyr[2] + bq * p.ps[2] + tile_off(y2, x2, p.tx[2]);
-            *reinterpret_cast<float4*>(t2) = make_float4(l2[0][0], l2[0][1], l2[0][2], l2[0][3]);
-            *reinterpret_cast<float4*>(t2 + 4) = make_float4(l2[1][0], l2[1][1], l2[1][2], l2[1][3]);
-          }
-          if (p.levels > 3) {
-            const float a = ((l2[0][0] + l2[0][1]) + (l2[1][0] + l2[1][1])) * 0.25f;
-            const float c = ((l2[0][2] + l2[0][3]) + (l2[1][2] + l2[1][3])) * 0.25f;
-            const int y3 = y0 >> 3, x3 = x0 >> 3;  // x3 is even: both values sit in one tile row
-            if (y3 < p.Hl[3] && x3 < p.Wl[3])
-              *reinterpret_cast<float2*>(p.pyr[3] + bq * p.ps[3] + tile_off(y3, x3, p.tx[3])) = make_float2(a, c);
           }
         }
       }
     }
-    if (p.prof && lane == 0 && ew == 2) {  // warp 4 = TMEM lanes 0-31
-      p.prof[blockIdx.x * 16 + 7] = clock64() - t_begin;
+    if (p.prof && lane == 0 && ew == 2) {  // warp 4 = TMEM lanes 0-31, level-0 role
+      p.prof[blockIdx.x * 16 + 7] = clock64() - clk0;
       p.prof[blockIdx.x * 16 + 8] = w_full;
       p.prof[blockIdx.x * 16 + 9] = w_st;
       p.prof[blockIdx.x * 16 + 10] = w_ld;
       p.prof[blockIdx.x * 16 + 11] = tile;
     }
-    if (lane == 0) tma_store_wait_all();
-  } else if (TS) {
-    // =============================== A loaders (TS kernel): global -> registers -> tensor memory =========
-    // Warp w may touch TMEM lanes 32*(w%4)..+31 = queries of the 128-query tile; lane i copies the packed bf16 row
-    // of its query (Kp/2 32-bit words per part) into columns [part*Kp/2, ...) of its TMEM lane.
-    const int lane_q = (warp & 3) * 32;
-    const int words = p.Kp >> 1;  // 32-bit words per row and part (multiple of 32)
-    uint32_t nunit = 0;
-    for (int u = blockIdx.x; u < p.units; u += gridDim.x, ++nunit) {
-      const UnitCoord uc = decode_unit(p, u);
-      const int q = uc.mt * BM + lane_q + lane;
-      const bool q_ok = q < p.Q;
-      for (int part = 0; part < p.parts; ++part) {
-        // all loads of a part are in flight before the first store (128 registers at Kp = 256); the loads of
-        // part 0 are issued before waiting for the previous unit to release A
-        const uint4* row = reinterpret_cast<const uint4*>(
-            p.a_pack + (((long long)part * p.B + uc.b) * p.Q + (q_ok ? q : 0)) * words);
-        uint32_t r[MAX_KB][32];
-#pragma unroll
-        for (int ch = 0; ch < MAX_KB; ++ch) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            uint4 v = make_uint4(0u, 0u, 0u, 0u);
-            if (q_ok && ch * 32 < words) v = __ldg(row + ch * 8 + i);
-            r[ch][4 * i + 0] = v.x; r[ch][4 * i + 1] = v.y; r[ch][4 * i + 2] = v.z; r[ch][4 * i + 3] = v.w;
-          }
-        }
-        if (part == 0 && nunit > 0) mbar_wait(a_empty, (nunit - 1) & 1);  // previous unit's MMAs are done with A
-        if (part == 0) tc_fence_after();
-#pragma unroll
-        for (int ch = 0; ch < MAX_KB; ++ch)
-          if (ch * 32 < words) tmem_st32(tmem_base + ((uint32_t)lane_q << 16) + part * words + ch * 32, r[ch]);
-      }
-      tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(a_full);
+    if (p.prof && lane == 0 && ew == 6) {  // warp 8 = TMEM lanes 0-31, pooled-levels role
+      p.prof[blockIdx.x * 16 + 12] = clock64() - clk0;
+      p.prof[blockIdx.x * 16 + 13] = w_full;
     }
+    if (lane == 0) tma_store_wait_all();
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (NCTA == 2) cluster_sync_all();  // the leader's MMAs read the peer's shared and tensor memory until the end
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    tmem_dealloc<NCTA>(tmem_base, 512);
   }
 }
 
-// ---- host side -------------------------------------------------------------------------------
 }  // namespace tc
 
 static int padded_k(int C) { return (C + tc::BK - 1) / tc::BK * tc::BK; }
@@ -625,17 +700,45 @@ size_t build_tc_workspace_bytes(int B, int C, int H, int W, int mode) {
   return (size_t)2 * parts * B * H * W * padded_k(C) * sizeof(__nv_bfloat16);
 }
 
+template <int NCTA>
+static int launch_main(const CUtensorMap& map_b, const CUtensorMap& map_l0, const CUtensorMap& map_l1, tc::Params& p,
+                       int grid, int smem_total, cudaStream_t s) {
+  using namespace tc;
+  cudaError_t e = cudaFuncSetAttribute(build_tc_kernel<NCTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET);
+  if (e != cudaSuccess) return (int)e;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = (size_t)smem_total;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = NCTA;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  e = cudaLaunchKernelEx(&cfg, build_tc_kernel<NCTA>, map_b, map_l0, map_l1, p);
+  if (e != cudaSuccess) return (int)e;
+  return launch_status();
+}
+
 int launch_build_tc(const float* f1, const float* f2, void* const* pyr, const rcb_pyramid_layout& lay, int B,
                     int C, int H, int W, int mode, void* ws, size_t ws_bytes, cudaStream_t s) {
   using namespace tc;
   if (lay.dtype != RCB_F32) return RCB_ERR_UNSUPPORTED;
   const int Kp = padded_k(C);
-  if (Kp > MAX_KB * BK) return RCB_ERR_UNSUPPORTED;  // A tile must stay resident (C <= 256)
+  if (Kp > MAX_KB * BK) return RCB_ERR_UNSUPPORTED;  // A must stay resident in tensor memory (C <= 256)
   if (!encode_fn()) return RCB_ERR_NO_DEVICE;
   const int parts = mode == RCB_BUILD_BF16X3 ? 2 : 1;
   const size_t need = build_tc_workspace_bytes(B, C, H, W, mode);
   if (!ws || ws_bytes < need || (reinterpret_cast<uintptr_t>(ws) & 127)) return RCB_ERR_WORKSPACE;
   const int Q = H * W;
+  // CTAs per MMA.  Both forms are verified by the tests; on B200 the kernel is bound by its stores under the 1 kW
+  // power cap, where coupling two SMs costs more than the halved B traffic saves (cfg2: 643 us vs 693 us), so
+  // single-CTA MMAs are the default.  RCB_TC_NCTA=2 selects the pairs.
+  static const int ncta_env = [] { const char* e = getenv("RCB_TC_NCTA"); return e ? atoi(e) : 1; }();
+  const int ncta = ncta_env == 2 ? 2 : 1;
 
   // 1. pack: fp32 NCHW -> bf16 hi/lo, K-major
   __nv_bfloat16* packed = static_cast<__nv_bfloat16*>(ws);
@@ -649,18 +752,11 @@ int launch_build_tc(const float* f1, const float* f2, void* const* pyr, const rc
   const __nv_bfloat16* b_pack = packed + (size_t)parts * B * Q * Kp;
 
   // 2. tensor maps
-  CUtensorMap map_a, map_b, map_l0, map_l1;
-  {
-    cuuint64_t dims[3] = {(cuuint64_t)Kp, (cuuint64_t)Q, (cuuint64_t)parts * B};
-    cuuint64_t str[2] = {(cuuint64_t)Kp * 2, (cuuint64_t)Q * Kp * 2};
-    cuuint32_t box[3] = {BK, BM, 1};
-    if (!encode(&map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, a_pack, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B))
-      return RCB_ERR_INVALID_ARGUMENT;
-  }
+  CUtensorMap map_b, map_l0, map_l1;
   {
     cuuint64_t dims[4] = {(cuuint64_t)Kp, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)parts * B};
     cuuint64_t str[3] = {(cuuint64_t)Kp * 2, (cuuint64_t)W * Kp * 2, (cuuint64_t)Q * Kp * 2};
-    cuuint32_t box[4] = {BK, PW, PH, 1};
+    cuuint32_t box[4] = {BK, PW, (cuuint32_t)(PH / ncta), 1};  // each CTA of a pair loads half of the patch rows
     if (!encode(&map_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, b_pack, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B))
       return RCB_ERR_INVALID_ARGUMENT;
   }
@@ -679,39 +775,18 @@ int launch_build_tc(const float* f1, const float* f2, void* const* pyr, const rc
       return RCB_ERR_INVALID_ARGUMENT;
   }
 
-  CUtensorMap map_seq = map_l0;
-  long long seq_chunks = lay.level_bytes[0] / 4096;
-  {
-    const char* skip = getenv("RCB_TC_DEBUG_SKIP");
-    if (skip && (atoi(skip) & 1024)) {
-      cuuint64_t dims[2] = {32, (cuuint64_t)seq_chunks * 32};
-      cuuint64_t str[1] = {128};
-      cuuint32_t box[2] = {32, 32};
-      if (!encode(&map_seq, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, pyr[0], dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B))
-        return RCB_ERR_INVALID_ARGUMENT;
-    }
-  }
-
-  // 3. work decomposition: unit = (batch, 128-query tile, group of patches); A stays resident per unit
+  // 3. work decomposition
   Params p{};
   p.B = B; p.C = C; p.H = H; p.W = W; p.Q = Q;
   p.kblocks = Kp / BK;
   p.parts = parts;
   p.levels = lay.levels;
   p.mtiles = (Q + BM - 1) / BM;
+  p.mgroups = (p.mtiles + ncta - 1) / ncta;
   p.pcols = (W + PW - 1) / PW;
   p.prows = (H + PH - 1) / PH;
-  const int npatch = p.pcols * p.prows;
-  const int base_units = B * p.mtiles;
-  int groups = 1;
-  // aim for >= 3 units per SM so the static round-robin balances, but keep >= 4 patches per A load
-  while (groups < npatch && base_units * groups < 3 * kNumSMs && (npatch + groups) / (groups + 1) >= 4) ++groups;
-  p.patches_per_group = (npatch + groups - 1) / groups;
-  p.groups = (npatch + p.patches_per_group - 1) / p.patches_per_group;
-  p.units = base_units * p.groups;
+  p.npatch = p.pcols * p.prows;
   p.scale = 1.0f / sqrtf((float)C);
-  const char* dbg = getenv("RCB_TC_DIRECT_STORE");
-  p.direct_store = (dbg && dbg[0] == '1') ? 1 : 0;
   const char* prof = getenv("RCB_TC_PROF_PTR");  // debug: device buffer of 16 x 148 uint64 supplied by tools/time_build.py
   p.prof = prof ? reinterpret_cast<unsigned long long*>(strtoull(prof, nullptr, 0)) : nullptr;
   const char* skip = getenv("RCB_TC_DEBUG_SKIP");
@@ -720,46 +795,42 @@ int launch_build_tc(const float* f1, const float* f2, void* const* pyr, const rc
     p.pyr[l] = l < lay.levels ? static_cast<float*>(pyr[l]) : nullptr;
     p.Hl[l] = lay.H[l]; p.Wl[l] = lay.W[l]; p.tx[l] = lay.tiles_x[l]; p.ps[l] = lay.plane_stride[l];
   }
-
-  const char* ss = getenv("RCB_TC_SS");  // debug: keep A in shared memory (SS MMA) instead of tensor memory
-  const bool ts = !(ss && ss[0] == '1');
   p.Kp = Kp;
   p.a_pack = reinterpret_cast<const uint32_t*>(a_pack);
-  if (ts) {
-    p.acc_col0 = (parts * (Kp / 2) + 127) / 128 * 128;  // A occupies the first parts*Kp/2 TMEM columns
-    p.nacc = (512 - p.acc_col0) / BN < MAX_ACC ? (512 - p.acc_col0) / BN : MAX_ACC;
-  } else {
-    p.acc_col0 = 0;
-    p.nacc = MAX_ACC;
-  }
-  const int a_bytes = ts ? 0 : parts * p.kblocks * A_TILE_BYTES;
-  int nstg = 4;
+  p.acc_col0 = (parts * (Kp / 2) + 127) / 128 * 128;  // A occupies the first parts*Kp/2 TMEM columns
+  p.nacc = (512 - p.acc_col0) / BN < MAX_ACC ? (512 - p.acc_col0) / BN : MAX_ACC;
+
+  int nstg = 2;
   if (const char* e = getenv("RCB_TC_NSTG")) nstg = atoi(e);
-  if (nstg != 2 && nstg != 3 && nstg != 4 && nstg != 6 && nstg != 8) nstg = 4;
+  if (nstg != 2 && nstg != 3 && nstg != 4 && nstg != 6) nstg = 2;
   p.nstg = nstg;
-  const int STG_TOTAL = NUM_EPI_WARPS * nstg * STG_BYTES;
-  int nstage = (SMEM_BUDGET - BAR_BYTES - STG_TOTAL - a_bytes) / STAGE_BYTES;
+  const int stg_total = 2 * NUM_EPI_WARPS * nstg * STG_BYTES;
+  const int stage_bytes = BOXES_PER_STAGE * B_TILE_BYTES / ncta;
+  int nstage = (SMEM_BUDGET - BAR_BYTES - stg_total) / stage_bytes;
   if (nstage > MAX_STAGE) nstage = MAX_STAGE;
   if (const char* ns = getenv("RCB_TC_NSTAGE")) nstage = atoi(ns) < nstage ? atoi(ns) : nstage;
   if (nstage < 2) return RCB_ERR_UNSUPPORTED;
   p.nstage = nstage;
-  p.b_off = a_bytes;
-  p.stg_off = p.b_off + nstage * STAGE_BYTES;
-  p.bar_off = p.stg_off + STG_TOTAL;
+  p.b_off = 0;
+  p.stg_off = p.b_off + nstage * stage_bytes;
+  p.bar_off = p.stg_off + stg_total;
   const int smem_total = p.bar_off + BAR_BYTES;
 
-  const int grid = p.units < kNumSMs ? p.units : kNumSMs;
-  p.seq_chunks_per_cta = (int)(seq_chunks / grid);
-  if (ts) {
-    cudaError_t e = cudaFuncSetAttribute(build_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET);
-    if (e != cudaSuccess) return (int)e;
-    build_tc_kernel<true><<<grid, THREADS_TS, smem_total, s>>>(map_a, map_b, map_l0, map_l1, map_seq, p);
-  } else {
-    cudaError_t e = cudaFuncSetAttribute(build_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET);
-    if (e != cudaSuccess) return (int)e;
-    build_tc_kernel<false><<<grid, THREADS, smem_total, s>>>(map_a, map_b, map_l0, map_l1, map_seq, p);
-  }
-  return launch_status();
+  // one CTA per SM.  Units (batch, query-tile group) go round-robin over the clusters; what is left after the full
+  // rounds is cut along the patch sequence so that the last round is short instead of mostly idle.
+  const int units = B * p.mgroups;
+  int clusters = kNumSMs / ncta;
+  if (clusters > units * p.npatch) clusters = units * p.npatch;
+  p.full_rounds = units / clusters;
+  const int left = units % clusters;
+  p.tail_split = left ? clusters / left : 1;
+  if (p.tail_split > p.npatch) p.tail_split = p.npatch;
+  p.tail_len = (p.npatch + p.tail_split - 1) / p.tail_split;
+  p.tail_split = (p.npatch + p.tail_len - 1) / p.tail_len;
+  p.tail_pieces = left * p.tail_split;
+  const int grid = clusters * ncta;
+  return ncta == 2 ? launch_main<2>(map_b, map_l0, map_l1, p, grid, smem_total, s)
+                   : launch_main<1>(map_b, map_l0, map_l1, p, grid, smem_total, s);
 }
 
 }  // namespace rcb

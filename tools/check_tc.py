@@ -1,5 +1,5 @@
 """On-GPU cross-check of the tcgen05 build modes against the fp32 SIMT build (level by level).
-    python tools/check_tc.py            # several shapes, TMA stores and the debug direct-store path"""
+    python tools/check_tc.py            # several shapes; RCB_TC_NCTA=2 selects the cta_group::2 pair kernel"""
 import os
 import sys
 
@@ -12,8 +12,7 @@ dev = torch.device("cuda:0")
 shapes = [(1, 64, 16, 16, 4), (2, 24, 11, 13, 3), (1, 128, 24, 40, 4), (2, 256, 55, 128, 4), (1, 256, 47, 156, 4),
           (1, 32, 8, 8, 1)]
 ok = True
-for direct in ("1", "0"):
-    os.environ["RCB_TC_DIRECT_STORE"] = direct
+for direct in ("0",):
     for (B, C, H, W, L) in shapes:
         g = torch.Generator(device="cpu").manual_seed(7)
         f1 = (0.75 * torch.randn(B, C, H, W, generator=g)).to(dev)
@@ -24,7 +23,7 @@ for direct in ("1", "0"):
                 got = CorrBlock(f1, f2, num_levels=L, radius=4, mode=mode).corr_pyramid
                 torch.cuda.synchronize()
             except Exception as e:  # noqa: BLE001
-                print(f"direct={direct} {mode} {(B, C, H, W, L)}: EXCEPTION {e}")
+                print(f"ncta={os.environ.get("RCB_TC_NCTA", "1")} {mode} {(B, C, H, W, L)}: EXCEPTION {e}")
                 ok = False
                 raise SystemExit(1)
             errs = []
@@ -37,7 +36,7 @@ for direct in ("1", "0"):
                     bad = ((r - t).abs() > tol * r.abs().max()).nonzero()
                     print(f"   level {l}: {bad.shape[0]} bad of {r.numel()}, first {bad[:6].tolist()}, "
                           f"nan={torch.isnan(t).sum().item()}")
-            print(f"direct={direct} {mode:7s} {str((B, C, H, W, L)):24s} rel err per level:",
+            print(f"ncta={os.environ.get("RCB_TC_NCTA", "1")} {mode:7s} {str((B, C, H, W, L)):24s} rel err per level:",
                   " ".join(f"{e:.2e}" for e in errs), "OK" if all(e < tol for e in errs) else "FAIL")
 print("ALL OK" if ok else "SOME FAILED")
 sys.exit(0 if ok else 1)

@@ -43,8 +43,8 @@ if os.environ.get("RCB_TC_PROF") == "1":
     torch.cuda.synchronize()
     del os.environ["RCB_TC_PROF_PTR"]
     pr = prof.view(148, 16).double()
-    names = ["prod_total", "prod_wait_b_empty", "prod_wait_a_empty", "mma_total", "mma_wait_b_full", "mma_wait_acc_empty",
-             "mma_wait_a_full", "epi_total", "epi_wait_acc_full", "epi_wait_store_read", "epi_tmem_ld", "tiles"]
+    names = ["prod_total", "prod_wait_b_empty", "unused", "mma_total", "mma_wait_b_full", "mma_wait_acc_empty",
+             "mma_wait_a_full", "epi_total", "epi_wait_acc_full", "epi_wait_store_read", "epi_tmem_ld", "tiles", "pool_total", "pool_wait_acc_full"]
     print("per-CTA mean cycles:", {n: int(pr[:, i].mean().item()) for i, n in enumerate(names)})
 print(f"{a.config} {a.mode} skip={os.environ.get('RCB_TC_DEBUG_SKIP','0')} nstage={os.environ.get('RCB_TC_NSTAGE','-')} "
       f"build {e0.elapsed_time(e1) / a.reps * 1e3:.1f} us (host enqueue {1e6 * (t1 - t0) / a.reps:.1f} us/call)")
