@@ -318,7 +318,7 @@ def run_ours(args, cfg):
                      "unit": "GB/s", "frac": lookup_gbs / hbm_peak, "traffic": ncu_traffic("lookup"),
                      "peak_source": peak_kind, "us_per_launch": lookup_ms * 1e3,
                      "algorithmic_bytes_per_launch": lookup_bytes},
-        "roofline_build": {"kernel": f"corr_build[{args.mode}]", "bound": "hbm", "achieved": build_gbs,
+        "roofline_build": {"kernel": f"pack_operands_kernel + build_tc_kernel<1> [{args.mode}]", "bound": "hbm", "achieved": build_gbs,
                            "peak": hbm_peak, "unit": "GB/s", "frac": build_gbs / hbm_peak,
                            "tensor_tflops": build_tflops, "tensor_frac_of_bf16_sustained": build_tflops / tc_peak,
                            "traffic": ncu_traffic("build"), "us_per_launch": build_ms * 1e3,
@@ -342,7 +342,7 @@ def run_ours(args, cfg):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))
