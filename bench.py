@@ -28,6 +28,7 @@ CONFIGS = {
     "cfg1": (1, 128, 55, 128, 3, 4, 12, "RAFT-small Sintel 436x1024(->440x1024), 12 iters"),
     "cfg2": (8, 256, 55, 128, 4, 4, 32, "RAFT-full Sintel 440x1024, batch 8/GPU, 32 iters"),
     "cfg3": (16, 256, 47, 156, 4, 4, 24, "RAFT-full KITTI 376x1248, batch 16/GPU, 24 iters"),
+    "cfg4": (4, 256, 136, 240, 4, 4, 32, "RAFT-full 1088x1920 (1080p padded), batch 4/GPU, 32 iters"),
     "cfg5": (12, 256, 46, 62, 4, 4, 12, "RAFT-full FlyingChairs 368x496, batch 12/GPU, 12 iters"),
 }
 SEED = 1234  # the reference's own seed (train.py:294)

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define RCB_ABI_VERSION 3
+#define RCB_ABI_VERSION 4
 #define RCB_MAX_LEVELS 4 /* core/raft.py:46-53 fixes corr_levels = 4 */
 #define RCB_MAX_RADIUS 4 /* core/raft.py:47,53: radius 3 (small) / 4 (full) */
 
@@ -131,6 +131,13 @@ RCB_API int rcb_corr_lookup_backward(const void* const* pyr, const float* coords
 RCB_API int rcb_corr_pool_backward(float* const* dpyr, int B, int H, int W, int levels, rcb_stream_t stream);
 RCB_API int rcb_corr_contract_backward(const float* fmap1, const float* fmap2, const float* dvol0, float* dfmap1,
                                float* dfmap2, int B, int C, int H, int W, rcb_stream_t stream);
+/* The same two GEMMs on the tensor cores (tcgen05, hi/lo bf16 split with fp32 accumulation, ~5e-6 of max-abs;
+ * C <= 256).  `workspace` (>= rcb_corr_contract_backward_tc_workspace_bytes(), 256-byte aligned) holds the packed
+ * bf16 operands: dV0 and its transpose, fmap1 and fmap2. */
+RCB_API size_t rcb_corr_contract_backward_tc_workspace_bytes(int B, int C, int H, int W);
+RCB_API int rcb_corr_contract_backward_tc(const float* fmap1, const float* fmap2, const float* dvol0, float* dfmap1,
+                                  float* dfmap2, int B, int C, int H, int W, void* workspace,
+                                  size_t workspace_bytes, rcb_stream_t stream);
 
 /* ---- K3 / K5: on-the-fly correlation (the alt_cuda_corr extension) ------------------------
  * rcb_altcorr_forward replaces alt_cuda_corr.forward (correlation.cpp:23-33,

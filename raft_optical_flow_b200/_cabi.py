@@ -9,7 +9,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libraftcorr_b200.so")
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 MAX_LEVELS = 4
 MAX_RADIUS = 4
 
@@ -51,6 +51,8 @@ SIGNATURES = {
     "rcb_corr_lookup_backward": (_i, [ctypes.POINTER(_vp), _vp, _vp, ctypes.POINTER(_vp), _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "rcb_corr_pool_backward": (_i, [ctypes.POINTER(_vp), _i, _i, _i, _i, _vp]),
     "rcb_corr_contract_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "rcb_corr_contract_backward_tc_workspace_bytes": (ctypes.c_size_t, [_i, _i, _i, _i]),
+    "rcb_corr_contract_backward_tc": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, ctypes.c_size_t, _vp]),
     "rcb_altcorr_forward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "rcb_altcorr_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "rcb_altcorr_prepare": (_i, [_vp, _vp, _vp, ctypes.POINTER(_vp), _i, _i, _i, _i, _i, _vp]),

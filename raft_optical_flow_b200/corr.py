@@ -99,9 +99,18 @@ class _BuildFn(torch.autograd.Function):
         with torch.cuda.device(st.f1.device):
             s = _stream(st.f1)
             _cabi.check(lib.rcb_corr_pool_backward(st.dpyr.ptrs, B, H, W, st.levels, s), "rcb_corr_pool_backward")
-            _cabi.check(lib.rcb_corr_contract_backward(st.f1.data_ptr(), st.f2.data_ptr(), st.dpyr.bufs[0].data_ptr(),
-                                                       df1.data_ptr(), df2.data_ptr(), B, C, H, W, s),
-                        "rcb_corr_contract_backward")
+            if st.mode == _cabi.BUILD_FP32_SIMT or C > 256:  # the reference's exact arithmetic class: fp32 FMA tiles
+                _cabi.check(lib.rcb_corr_contract_backward(st.f1.data_ptr(), st.f2.data_ptr(), st.dpyr.bufs[0].data_ptr(),
+                                                           df1.data_ptr(), df2.data_ptr(), B, C, H, W, s),
+                            "rcb_corr_contract_backward")
+            else:  # tensor cores, hi/lo bf16 split like the forward build
+                nws = lib.rcb_corr_contract_backward_tc_workspace_bytes(B, C, H, W)
+                ws = torch.empty(max(nws, 256), dtype=torch.uint8, device=st.f1.device)
+                _cabi.check(lib.rcb_corr_contract_backward_tc(st.f1.data_ptr(), st.f2.data_ptr(),
+                                                              st.dpyr.bufs[0].data_ptr(), df1.data_ptr(), df2.data_ptr(),
+                                                              B, C, H, W, ws.data_ptr(), nws, s),
+                            "rcb_corr_contract_backward_tc")
+                ws.record_stream(torch.cuda.current_stream(st.f1.device))
         st.dpyr = None  # a second backward pass starts from zero again
         return df1, df2, None
 
@@ -140,7 +149,7 @@ class _State:
 
     def __init__(self, f1, f2, levels, radius, mode, pyr_dtype):
         B, C, H, W = f1.shape
-        self.f1, self.f2, self.levels, self.radius = f1, f2, levels, radius
+        self.f1, self.f2, self.levels, self.radius, self.mode = f1, f2, levels, radius, mode
         self.pyr = _Pyramid(B, H, W, levels, f1.device, pyr_dtype)
         self.dpyr = None
         _build(f1, f2, levels, mode, self.pyr)

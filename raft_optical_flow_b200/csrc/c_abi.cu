@@ -115,6 +115,21 @@ int rcb_corr_contract_backward(const float* fmap1, const float* fmap2, const flo
                                   reinterpret_cast<cudaStream_t>(stream));
 }
 
+size_t rcb_corr_contract_backward_tc_workspace_bytes(int B, int C, int H, int W) {
+  if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return 0;
+  return contract_backward_tc_workspace_bytes(B, C, H, W);
+}
+
+int rcb_corr_contract_backward_tc(const float* fmap1, const float* fmap2, const float* dvol0, float* dfmap1,
+                                  float* dfmap2, int B, int C, int H, int W, void* workspace,
+                                  size_t workspace_bytes, rcb_stream_t stream) {
+  if (!fmap1 || !fmap2 || !dvol0 || !dfmap1 || !dfmap2 || B <= 0 || C <= 0 || H <= 0 || W <= 0)
+    return RCB_ERR_INVALID_ARGUMENT;
+  if (!aligned16(dvol0)) return RCB_ERR_INVALID_ARGUMENT;
+  return launch_contract_backward_tc(fmap1, fmap2, dvol0, dfmap1, dfmap2, B, C, H, W, workspace, workspace_bytes,
+                                     reinterpret_cast<cudaStream_t>(stream));
+}
+
 int rcb_altcorr_forward(const float* fmap1, const float* fmap2, const float* coords, float* corr, int B, int N,
                         int H1, int W1, int H2, int W2, int C, int radius, rcb_stream_t stream) {
   if (!fmap1 || !fmap2 || !coords || !corr) return RCB_ERR_INVALID_ARGUMENT;

@@ -123,6 +123,9 @@ int launch_lookup_backward(const void* const* pyr, const rcb_pyramid_layout& lay
 int launch_pool_backward(float* const* dpyr, const rcb_pyramid_layout& lay, int B, int H, int W, cudaStream_t s);
 int launch_contract_backward(const float* f1, const float* f2, const float* dvol0, float* df1, float* df2, int B,
                              int C, int H, int W, cudaStream_t s);
+size_t contract_backward_tc_workspace_bytes(int B, int C, int H, int W);
+int launch_contract_backward_tc(const float* f1, const float* f2, const float* dvol0, float* df1, float* df2, int B,
+                                int C, int H, int W, void* ws, size_t ws_bytes, cudaStream_t s);
 int launch_altcorr_forward(const float* f1, const float* f2, const float* coords, float* corr, int B, int N, int H1,
                            int W1, int H2, int W2, int C, int r, cudaStream_t s);
 int launch_altcorr_backward(const float* f1, const float* f2, const float* coords, const float* cg, float* g1,
