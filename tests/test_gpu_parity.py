@@ -103,15 +103,16 @@ def test_real_features_golden(rcb, dev):
             assert rel_err(alt(c)[:, :, ::2, ::2].cpu().numpy(), g["out_sub"][k]) < TOL
 
 
+@pytest.mark.parametrize("mode", PARITY_MODES)  # fp32: SIMT contraction backward, bf16x3: the tcgen05 GEMMs
 @pytest.mark.parametrize("name", ["corrblock_odd", "corrblock_full_r4"])
-def test_corrblock_backward_golden(rcb, dev, name):
+def test_corrblock_backward_golden(rcb, dev, name, mode):
     """Gradients w.r.t. fmap1, fmap2 AND coords vs autograd through the reference CorrBlock."""
     g = load_golden(name)
     B, C, H, W, L, r, seed = [int(v) for v in g["meta"]]
     f1 = t(g["fmap1"], dev).requires_grad_(True)
     f2 = t(g["fmap2"], dev).requires_grad_(True)
     co = t(g["coords"], dev).requires_grad_(True)
-    blk = rcb.CorrBlock(f1, f2, num_levels=L, radius=r, mode="fp32")
+    blk = rcb.CorrBlock(f1, f2, num_levels=L, radius=r, mode=mode)
     out = blk(co)
     out.backward(t(cotangent(seed, g["out"].shape), dev))
     assert rel_err(f1.grad.cpu().numpy(), g["df1"]) < GRAD_TOL
@@ -119,14 +120,16 @@ def test_corrblock_backward_golden(rcb, dev, name):
     assert rel_err(co.grad.cpu().numpy(), g["dcoords"]) < GRAD_TOL
 
 
-def test_backward_accumulates_over_iterations(rcb, dev, orc):
+@pytest.mark.parametrize("mode", PARITY_MODES)
+@pytest.mark.parametrize("dims", [(1, 16, 12, 16), (2, 24, 11, 13), (1, 200, 23, 39)])  # odd sizes, C not a multiple of 16
+def test_backward_accumulates_over_iterations(rcb, dev, orc, dims, mode):
     """train.py runs 12 lookups per forward; their gradients must add up in one backward pass."""
-    f1n, f2n, c0 = seeded(5, 1, 16, 12, 16, sigma=2.0)
-    _, _, c1 = seeded(6, 1, 16, 12, 16, sigma=2.0)
+    f1n, f2n, c0 = seeded(5, *dims, sigma=2.0)
+    _, _, c1 = seeded(6, *dims, sigma=2.0)
     L, r = 3, 3
     f1 = t(f1n, dev).requires_grad_(True)
     f2 = t(f2n, dev).requires_grad_(True)
-    blk = rcb.CorrBlock(f1, f2, num_levels=L, radius=r, mode="fp32")
+    blk = rcb.CorrBlock(f1, f2, num_levels=L, radius=r, mode=mode)
     o0, o1 = blk(t(c0, dev)), blk(t(c1, dev))
     g0, g1 = cotangent(11, tuple(o0.shape)), cotangent(12, tuple(o1.shape))
     (o0 * t(g0, dev)).sum().add((o1 * t(g1, dev)).sum()).backward()
@@ -315,3 +318,47 @@ def test_runs_on_the_callers_stream(rcb, dev, orc):
         out = rcb.CorrBlock(a, b, mode="fp32")(c)
     s.synchronize()
     assert rel_err(out.cpu().numpy(), want) < TOL
+
+
+def test_planned_and_unplanned_lookup_agree(rcb, dev):
+    """rcb_corr_lookup encodes the TMA tensor maps per call, rcb_corr_lookup_planned reuses a caller-owned plan:
+    same kernel, bit-identical output (also exercises the raw C ABI without the Python mirror)."""
+    from raft_optical_flow_b200 import _cabi
+    f1n, f2n, cn = seeded(21, 2, 32, 19, 27)
+    L, r = 4, 4
+    blk = rcb.CorrBlock(t(f1n, dev), t(f2n, dev), num_levels=L, radius=r)
+    c = t(cn, dev)
+    want = blk(c)
+    got = torch.empty_like(want)
+    st = blk._state
+    s = torch.cuda.current_stream(dev).cuda_stream
+    _cabi.check(_cabi.lib().rcb_corr_lookup(st.pyr.ptrs, c.data_ptr(), got.data_ptr(), 2, 19, 27, L, r, _cabi.F32, s),
+                "rcb_corr_lookup")
+    torch.cuda.synchronize()
+    assert torch.equal(got, want)
+
+
+def test_cta_pair_build_matches_single_cta(dev):
+    """RCB_TC_NCTA=2 (tcgen05.mma.cta_group::2 pairs) is read once per process: run it in a child process and compare
+    the pyramid with this process's single-CTA build, level by level."""
+    import subprocess
+    import sys
+    import tempfile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, numpy as np, torch\n"
+        f"sys.path.insert(0, {root!r})\n"
+        "from raft_optical_flow_b200 import CorrBlock\n"
+        "rs = np.random.RandomState(3)\n"
+        "f1 = torch.from_numpy((0.75 * rs.standard_normal((2, 256, 47, 78))).astype(np.float32)).cuda()\n"
+        "f2 = torch.from_numpy((0.75 * rs.standard_normal((2, 256, 47, 78))).astype(np.float32)).cuda()\n"
+        "pyr = CorrBlock(f1, f2, num_levels=4, radius=4, mode='bf16x3').corr_pyramid\n"
+        "torch.save([p.contiguous().cpu() for p in pyr], sys.argv[1])\n")
+    outs = []
+    for ncta in ("1", "2"):
+        with tempfile.NamedTemporaryFile(suffix=".pt") as f:
+            env = dict(os.environ, RCB_TC_NCTA=ncta)
+            subprocess.run([sys.executable, "-c", code, f.name], check=True, env=env, timeout=300)
+            outs.append(torch.load(f.name))
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)  # same products in the same order: bit-identical
