@@ -302,6 +302,95 @@ lookup_backward_kernel(PyramidDev pyr, PyramidDev dpyr, const float* __restrict_
   }
 }
 
+// Pyramid-gradient half of the lookup backward, restructured like the forward kernel: CTA = 32 consecutive queries
+// of ONE level, 4 lanes per query.  The resampling is separable, so is its transpose:
+//   dh[j][a] = gy * G[a][j] + fy * G[a][j-1]        (G = grad_out of this level, (2r+1) x (2r+1))
+//   dW[j][i] = gx * dh[j][i] + fx * dh[j][i-1]      (dW = gradient of the (2r+2)^2 tap window)
+// The 4 lanes of a query split the window rows; a row is aligned to the 16-byte tile rows of the plane with two
+// select stages and added with red.global.add.v4.f32 -- one 16-byte reduction per tile row instead of four scalar
+// atomics per window entry (planes of different queries never alias; several GRU iterations add into one buffer).
+template <int R>
+__global__ void __launch_bounds__(128)
+lookup_backward_dpyr_kernel(PyramidDev dpyr, const float* __restrict__ coords, const float* __restrict__ grad_out,
+                            int Q, int L) {
+  constexpr int RD = 2 * R + 1, ROWS = 2 * R + 2;
+  constexpr int NCH = (ROWS + 6) >> 2;  // 16-byte chunks a window row can overlap
+  const int tid = threadIdx.x;
+  const int l = blockIdx.y, b = blockIdx.z;
+  const int ql = tid >> 2, sub = tid & 3;
+  const int q = blockIdx.x * 32 + ql;
+  if (q >= Q) return;
+  const int Hl = l == 0 ? dpyr.H[0] : l == 1 ? dpyr.H[1] : l == 2 ? dpyr.H[2] : dpyr.H[3];
+  const int Wl = l == 0 ? dpyr.W[0] : l == 1 ? dpyr.W[1] : l == 2 ? dpyr.W[2] : dpyr.W[3];
+  const int tw = l == 0 ? dpyr.tiles_x[0] : l == 1 ? dpyr.tiles_x[1] : l == 2 ? dpyr.tiles_x[2] : dpyr.tiles_x[3];
+  const long long ps = l == 0 ? dpyr.plane_stride[0] : l == 1 ? dpyr.plane_stride[1]
+                     : l == 2 ? dpyr.plane_stride[2] : dpyr.plane_stride[3];
+  float* base = static_cast<float*>(const_cast<void*>(l == 0 ? dpyr.ptr[0] : l == 1 ? dpyr.ptr[1]
+                                                      : l == 2 ? dpyr.ptr[2] : dpyr.ptr[3]));
+  float* dplane = base + ((long long)b * Q + q) * ps;
+  const float cx = __ldg(coords + (long long)(b * 2 + 0) * Q + q);
+  const float cy = __ldg(coords + (long long)(b * 2 + 1) * Q + q);
+  const LevelCoord lc = level_coord<R>(cx, cy, l, Hl, Wl);
+  const int ph = lc.xs & 3, xa = lc.xs - ph;
+  const float fx = lc.fx, fy = lc.fy, gx = 1.0f - lc.fx, gy = 1.0f - lc.fy;
+  const int j0 = (ROWS * sub) >> 2, j1 = (ROWS * (sub + 1)) >> 2;  // window rows [j0, j1) of this lane
+  constexpr int NJ = (ROWS + 3) / 4;
+  const float* g = grad_out + (((long long)b * L + l) * RD * RD) * Q + q;  // G[a][bb] at g[(a * RD + bb) * Q]
+  // grad_out rows bb = j0 - 1 .. j1 - 1 (all x offsets a): loaded once, each read is a 32-byte sector per 8 queries
+  float G[NJ + 1][RD];
+#pragma unroll
+  for (int t = 0; t <= NJ; ++t) {
+    const int bb = j0 - 1 + t;
+    const bool ok = bb >= 0 && bb < RD && bb < j1;
+#pragma unroll
+    for (int a = 0; a < RD; ++a) G[t][a] = ok ? __ldg(g + (long long)(a * RD + bb) * Q) : 0.f;
+  }
+#pragma unroll
+  for (int t = 0; t < NJ; ++t) {
+    const int j = j0 + t;
+    if (j >= j1) break;
+    const int y = lc.ys + j;
+    if (y < 0 || y >= Hl) continue;
+    float dw[ROWS + 6];  // dW[i] at dw[3 + i], zeros around it
+#pragma unroll
+    for (int i = 0; i < ROWS + 6; ++i) dw[i] = 0.f;
+    {
+      float dh[RD];
+#pragma unroll
+      for (int a = 0; a < RD; ++a) dh[a] = gy * G[t + 1][a] + fy * G[t][a];  // G[t+1] = row bb = j, G[t] = row j - 1
+#pragma unroll
+      for (int i = 0; i < ROWS; ++i)
+        dw[3 + i] = (i < RD ? gx * dh[i] : 0.f) + (i >= 1 ? fx * dh[i - 1] : 0.f);
+    }
+    // w[k] = dW[k - ph] for chunk-aligned position k = 0 .. 4 * NCH - 1
+    float s1[4 * NCH + 1], w[4 * NCH];
+#pragma unroll
+    for (int k = 0; k < 4 * NCH + 1; ++k) {  // s1[k] = dW[k - 1 - (ph & 2)]
+      const float u0 = (k + 2 < ROWS + 6) ? dw[k + 2] : 0.f;   // dW[k - 1]
+      const float u2 = (k < ROWS + 6) ? dw[k] : 0.f;           // dW[k - 3]
+      s1[k] = (ph & 2) ? u2 : u0;
+    }
+#pragma unroll
+    for (int k = 0; k < 4 * NCH; ++k) w[k] = (ph & 1) ? s1[k] : s1[k + 1];  // dW[k - ph]
+    float* rowp = dplane + (((long long)(y >> 2) * tw) << 4) + ((y & 3) << 2);
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+      const int xc = xa + 4 * k;
+      if (xc < 0 || xc >= Wl) continue;
+      float4 v = make_float4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
+      if (xc + 3 >= Wl) {  // the chunk hangs over the right edge: nothing is added to the padding
+        if (xc + 1 >= Wl) v.y = 0.f;
+        if (xc + 2 >= Wl) v.z = 0.f;
+        v.w = 0.f;
+      }
+      if (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f)
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(rowp + ((xc >> 2) << 4)), "f"(v.x), "f"(v.y),
+                     "f"(v.z), "f"(v.w)
+                     : "memory");
+    }
+  }
+}
+
 int launch_lookup_backward(const void* const* pyr, const rcb_pyramid_layout& lay, const float* coords,
                            const float* grad_out, float* const* dpyr, float* dcoords, int B, int H, int W,
                            int radius, cudaStream_t s) {
@@ -310,12 +399,26 @@ int launch_lookup_backward(const void* const* pyr, const rcb_pyramid_layout& lay
   const PyramidDev dd = make_pyramid_dev(reinterpret_cast<const void* const*>(dpyr), lay);
   const long long nq = (long long)B * H * W;
   const unsigned grid = (unsigned)((nq + 3) / 4);
-  switch (radius) {
-    case 1: lookup_backward_kernel<1><<<grid, 128, 0, s>>>(pd, dd, coords, grad_out, dcoords, B, H, W, lay.levels, dpyr != nullptr); break;
-    case 2: lookup_backward_kernel<2><<<grid, 128, 0, s>>>(pd, dd, coords, grad_out, dcoords, B, H, W, lay.levels, dpyr != nullptr); break;
-    case 3: lookup_backward_kernel<3><<<grid, 128, 0, s>>>(pd, dd, coords, grad_out, dcoords, B, H, W, lay.levels, dpyr != nullptr); break;
-    case 4: lookup_backward_kernel<4><<<grid, 128, 0, s>>>(pd, dd, coords, grad_out, dcoords, B, H, W, lay.levels, dpyr != nullptr); break;
-    default: return RCB_ERR_UNSUPPORTED;
+  const int Q = H * W;
+  // pyramid gradient: the tiled red.v4 kernel; coords gradient (needs the forward taps): the per-entry kernel
+  if (dpyr != nullptr) {
+    dim3 g3((Q + 31) / 32, lay.levels, B);
+    switch (radius) {
+      case 1: lookup_backward_dpyr_kernel<1><<<g3, 128, 0, s>>>(dd, coords, grad_out, Q, lay.levels); break;
+      case 2: lookup_backward_dpyr_kernel<2><<<g3, 128, 0, s>>>(dd, coords, grad_out, Q, lay.levels); break;
+      case 3: lookup_backward_dpyr_kernel<3><<<g3, 128, 0, s>>>(dd, coords, grad_out, Q, lay.levels); break;
+      case 4: lookup_backward_dpyr_kernel<4><<<g3, 128, 0, s>>>(dd, coords, grad_out, Q, lay.levels); break;
+      default: return RCB_ERR_UNSUPPORTED;
+    }
+  }
+  if (dcoords != nullptr) {
+    switch (radius) {
+      case 1: lookup_backward_kernel<1><<<grid, 128, 0, s>>>(pd, dd, coords, grad_out, dcoords, B, H, W, lay.levels, 0); break;
+      case 2: lookup_backward_kernel<2><<<grid, 128, 0, s>>>(pd, dd, coords, grad_out, dcoords, B, H, W, lay.levels, 0); break;
+      case 3: lookup_backward_kernel<3><<<grid, 128, 0, s>>>(pd, dd, coords, grad_out, dcoords, B, H, W, lay.levels, 0); break;
+      case 4: lookup_backward_kernel<4><<<grid, 128, 0, s>>>(pd, dd, coords, grad_out, dcoords, B, H, W, lay.levels, 0); break;
+      default: return RCB_ERR_UNSUPPORTED;
+    }
   }
   return launch_status();
 }
