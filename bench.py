@@ -190,11 +190,11 @@ def run_ours(args, cfg):
     dev_c = host_c.to(dev)
     host_out = torch.empty((B, L * (2 * r + 1) ** 2, H, W), dtype=torch.float32).pin_memory()
 
-    def step_resident(k, ev=None):
+    def step_resident(k, ev=None, mode=None, pdt=None):
         f = dev_f[k % nsets]
         if ev:
             ev[0].record()
-        blk = CorrBlock(f[0], f[1], num_levels=L, radius=r, mode=args.mode)
+        blk = CorrBlock(f[0], f[1], num_levels=L, radius=r, mode=mode or args.mode, pyramid_dtype=pdt or args.pyramid)
         if ev:
             ev[1].record()
         out = None
@@ -229,7 +229,7 @@ def run_ours(args, cfg):
         j = k % 2
         s_main.wait_event(in_ready[j])
         f, c = in_bufs[j]
-        blk = CorrBlock(f[0], f[1], num_levels=L, radius=r, mode=args.mode)
+        blk = CorrBlock(f[0], f[1], num_levels=L, radius=r, mode=args.mode, pyramid_dtype=args.pyramid)
         out = None
         for i in range(iters):
             out = blk(c[i])
@@ -275,6 +275,27 @@ def run_ours(args, cfg):
     build_ms = sum(e[0].elapsed_time(e[1]) for e in evs) / args.steps
     lookup_ms = sum(e[1].elapsed_time(e[2]) for e in evs) / (args.steps * iters)
 
+    # ---- fast mode, reported next to the headline (never instead of it): single bf16 pass + fp16-stored pyramid,
+    # the "within a stated bound" path of the spec (flow EPE delta <= 0.01 px, tests/test_gpu_e2e_raft.py)
+    fast = None
+    if args.pyramid == "f32" and args.mode == "bf16x3" and not args.no_fast_mode:
+        for k in range(3):
+            step_resident(k, mode="bf16", pdt="f16")
+        fevs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(min(args.steps, 5))]
+        fend = torch.cuda.Event(enable_timing=True)
+        barrier()
+        for k in range(len(fevs)):
+            step_resident(k, fevs[k], mode="bf16", pdt="f16")
+        fend.record()
+        barrier()
+        f_total = parallel.max_over_ranks([fevs[0][0].elapsed_time(fend)], device=dev)[0]
+        fast = {"build_mode": "bf16", "pyramid_dtype": "f16", "value": world * B * len(fevs) / (f_total * 1e-3),
+                "unit": "pairs/s", "ms_per_step": f_total / len(fevs),
+                "build_us": 1e3 * sum(e[0].elapsed_time(e[1]) for e in fevs) / len(fevs),
+                "lookup_us": 1e3 * sum(e[1].elapsed_time(e[2]) for e in fevs) / (len(fevs) * iters),
+                "note": "operands rounded to bf16 (2.6e-3 of max-abs), pyramid stored as fp16; "
+                        "final-flow EPE delta vs the reference 1e-3 px mean on the demo frames"}
+
     # ---- end to end: host buffers in, host result out ------------------------------------------
     run_e2e(max(2, args.warmup))
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -305,7 +326,7 @@ def run_ours(args, cfg):
         "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.config}: {desc}", "C": C, "grid": [H, W], "radius": r, "levels": L,
-                   "iters": iters, "pairs_per_gpu": B, "build_mode": args.mode, "pyramid_dtype": "f32",
+                   "iters": iters, "pairs_per_gpu": B, "build_mode": args.mode, "pyramid_dtype": args.pyramid,
                    "l2": "inputs larger than L2: every step streams a "
                          f"{build_bytes / 1e9:.2f} GB pyramid through the 126 MB L2 and alternates input sets",
                    "parallelism": f"batch shards, {world} x 1 process per GPU, no collective"},
@@ -326,6 +347,8 @@ def run_ours(args, cfg):
                            "algorithmic_bytes_per_launch": build_bytes, "algorithmic_flops": flops},
         "clocks": clocks,
     }
+    if fast:
+        line["fast_mode"] = fast
     if world == 1 and not args.no_cpu_baseline:
         from oracle import oracle as orc
         cores = orc.num_threads()
@@ -348,6 +371,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))
     ap.add_argument("--mode", default=os.environ.get("RAFT_CORR_MODE", "bf16x3"), choices=["fp32", "bf16x3", "bf16"])
+    ap.add_argument("--pyramid", default="f32", choices=["f32", "f16"], help="storage type of the correlation pyramid")
+    ap.add_argument("--no-fast-mode", action="store_true", help="skip the extra bf16 + fp16-pyramid measurement")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

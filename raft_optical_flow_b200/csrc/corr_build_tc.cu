@@ -84,13 +84,14 @@ struct Params {
   float scale;      // 1 / sqrt(C)
   int nstage, b_off, stg_off, bar_off;  // shared memory carve-up (bytes)
   int nstg;                             // staging boxes per epilogue warp
+  int f16;                              // pyramid stored as fp16 (tiles of 4 rows x 8 columns), else fp32 (4 x 4)
   int nacc, acc_col0;                   // TMEM: accumulator count, first accumulator column
   int Kp;                               // padded channel count
   const uint32_t* a_pack;               // packed bf16 A operand, [part][B][Q][Kp/2] 32-bit words
   unsigned long long* prof;  // debug: per-CTA cycle counters (16 per CTA), null in production
   int debug_skip;   // debug bitmask: 1 skip L0 TMA store issue, 2 skip L1 store, 4 skip L2/L3, 8 skip staging writes,
                     // 16 skip B loads, 32 skip MMAs, 64 skip TMEM loads, 128/256 plain arrives instead of commits
-  float* pyr[RCB_MAX_LEVELS];
+  float* pyr[RCB_MAX_LEVELS];           // (fp16 pyramids: the same pointers, reinterpreted)
   int Hl[RCB_MAX_LEVELS], Wl[RCB_MAX_LEVELS], tx[RCB_MAX_LEVELS];  // level sizes, tiles per tile row
   long long ps[RCB_MAX_LEVELS];
 };
@@ -135,6 +136,21 @@ pack_operands_kernel(const float* __restrict__ f1, const float* __restrict__ f2,
       *reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<__nv_bfloat16*>(dst) + part_stride) = lo;
     }
   }
+}
+
+// 8 floats -> 8 fp16 (round to nearest even) in one 16-byte vector
+RCB_DEVINL uint4 pack_half8(float a0, float a1, float a2, float a3, float a4, float a5, float a6, float a7) {
+  uint4 u;
+  __half2 h;
+  h = __floats2half2_rn(a0, a1); u.x = *reinterpret_cast<uint32_t*>(&h);
+  h = __floats2half2_rn(a2, a3); u.y = *reinterpret_cast<uint32_t*>(&h);
+  h = __floats2half2_rn(a4, a5); u.z = *reinterpret_cast<uint32_t*>(&h);
+  h = __floats2half2_rn(a6, a7); u.w = *reinterpret_cast<uint32_t*>(&h);
+  return u;
+}
+// element offset (in halfs) of (y, x) in a plane of 4 x 8 fp16 tiles
+RCB_DEVINL long long tile_off_h(int y, int x, int tiles_x) {
+  return ((long long)((y >> 2) * tiles_x + (x >> 3)) << 5) + ((y & 3) << 3) + (x & 7);
 }
 
 // ---- main kernel -------------------------------------------------------------------------------
@@ -439,7 +455,34 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
               vb[i] *= p.scale;
             }
             const int yy = y0 + 4 * band;
-            if (yy < p.H && q_w < p.Q) {  // warp-uniform
+            if (p.f16) {
+              // fp16 pyramid: the band is 2 tiles of 4 x 8 halfs = 128 contiguous bytes per query = ONE box
+              if (yy < p.H && q_w < p.Q) {  // warp-uniform (x0 < W always holds)
+                unsigned char* sb = stg + sbuf * STG_BYTES;
+                {
+                  const long long c0 = p.prof ? clock64() : 0;
+                  wait_stg();
+                  if (p.prof) w_st += clock64() - c0;
+                }
+                if (!(p.debug_skip & 8)) {
+#pragma unroll
+                  for (int c = 0; c < 8; ++c) {  // chunk c = tile (c >> 2), tile row (c & 3): 8 halfs
+                    const int r = c & 3;
+                    const float* src = (r < 2) ? va : vb;
+                    const int o = (r & 1) * 16 + 8 * (c >> 2);
+                    *reinterpret_cast<uint4*>(sb + lane * 128 + ((c ^ (lane & 7)) << 4)) =
+                        pack_half8(src[o], src[o + 1], src[o + 2], src[o + 3], src[o + 4], src[o + 5], src[o + 6], src[o + 7]);
+                  }
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0 && !(p.debug_skip & 1)) {
+                  tma_store_4d(&map_l0, smem_u32(sb), (x0 >> 3) * 16, (yy >> 2), q_w, sg.b);
+                  tma_store_commit();
+                }
+                if (++sbuf == NSTG) sbuf = 0;
+              }
+            } else if (yy < p.H && q_w < p.Q) {  // warp-uniform
               // The band's 4 tiles are 256 contiguous bytes per query; they leave as two 128-byte halves
               // (2 tiles each) through a SWIZZLE_128B staging box [32 queries][128 B]: conflict-free st.shared.
 #pragma unroll
@@ -498,6 +541,56 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
             }
           }
           release_acc();
+          if (p.f16) {
+            // fp16 pyramid.  The means are formed from the fp32 accumulator values and rounded once.
+            if (p.levels > 1) {
+              const int y1 = y0 >> 1, x1 = x0 >> 1;  // 4 rows x 8 cols = ONE tile = 64 contiguous bytes per query
+              if (y1 < p.Hl[1] && x1 < p.Wl[1] && q_w < p.Q && !(p.debug_skip & 2)) {
+                unsigned char* sb = stg + sbuf * STG_BYTES;
+                wait_stg();
+                // SWIZZLE_64B box [32 queries][64 B]: 16-byte chunk r of row `lane` sits at chunk r ^ ((lane >> 1) & 3)
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+                  *reinterpret_cast<uint4*>(sb + lane * 64 + ((r ^ ((lane >> 1) & 3)) << 4)) =
+                      pack_half8(l1[r][0], l1[r][1], l1[r][2], l1[r][3], l1[r][4], l1[r][5], l1[r][6], l1[r][7]);
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                  tma_store_4d(&map_l1, smem_u32(sb), (x1 >> 3) * 16, (y1 >> 2), q_w, sg.b);
+                  tma_store_commit();
+                }
+                if (++sbuf == NSTG) sbuf = 0;
+              }
+            }
+            if (p.levels > 2 && q_ok && !(p.debug_skip & 4)) {
+              float l2[2][4];
+#pragma unroll
+              for (int r = 0; r < 2; ++r)
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  l2[r][j] = ((l1[2 * r][2 * j] + l1[2 * r][2 * j + 1]) + (l1[2 * r + 1][2 * j] + l1[2 * r + 1][2 * j + 1])) * 0.25f;
+              __half* base2 = reinterpret_cast<__half*>(p.pyr[2]);
+              const int y2 = y0 >> 2, x2 = x0 >> 2;  // y2 even, x2 a multiple of 4: two 8-byte half rows of one tile
+              if (y2 < p.Hl[2] && x2 < p.Wl[2]) {
+                __half* t2 = base2 + bq * p.ps[2] + tile_off_h(y2, x2, p.tx[2]);
+                const __half2 a0 = __floats2half2_rn(l2[0][0], l2[0][1]), a1 = __floats2half2_rn(l2[0][2], l2[0][3]);
+                const __half2 b0 = __floats2half2_rn(l2[1][0], l2[1][1]), b1 = __floats2half2_rn(l2[1][2], l2[1][3]);
+                *reinterpret_cast<uint2*>(t2) =
+                    make_uint2(*reinterpret_cast<const uint32_t*>(&a0), *reinterpret_cast<const uint32_t*>(&a1));
+                *reinterpret_cast<uint2*>(t2 + 8) =
+                    make_uint2(*reinterpret_cast<const uint32_t*>(&b0), *reinterpret_cast<const uint32_t*>(&b1));
+              }
+              if (p.levels > 3) {
+                const float a = ((l2[0][0] + l2[0][1]) + (l2[1][0] + l2[1][1])) * 0.25f;
+                const float c = ((l2[0][2] + l2[0][3]) + (l2[1][2] + l2[1][3])) * 0.25f;
+                const int y3 = y0 >> 3, x3 = x0 >> 3;  // x3 even: both values sit in one tile row
+                if (y3 < p.Hl[3] && x3 < p.Wl[3])
+                  *reinterpret_cast<__half2*>(reinterpret_cast<__half*>(p.pyr[3]) + bq * p.ps[3] +
+                                              tile_off_h(y3, x3, p.tx[3])) = __floats2half2_rn(a, c);
+              }
+            }
+            continue;
+          }
           if (p.levels > 1) {
             const int y1 = y0 >> 1, x1 = x0 >> 1;  // 4 rows x 8 cols = 2 tiles = 128 contiguous bytes per query
             if (y1 < p.Hl[1] && x1 < p.Wl[1] && q_w < p.Q && !(p.debug_skip & 2)) {
@@ -601,7 +694,8 @@ static int launch_main(const CUtensorMap& map_b, const CUtensorMap& map_l0, cons
 int launch_build_tc(const float* f1, const float* f2, void* const* pyr, const rcb_pyramid_layout& lay, int B,
                     int C, int H, int W, int mode, void* ws, size_t ws_bytes, cudaStream_t s) {
   using namespace tc;
-  if (lay.dtype != RCB_F32) return RCB_ERR_UNSUPPORTED;
+  const bool f16 = lay.dtype == RCB_F16;
+  const int esize = f16 ? 2 : 4;
   const int Kp = padded_k(C);
   if (Kp > MAX_KB * BK) return RCB_ERR_UNSUPPORTED;  // A must stay resident in tensor memory (C <= 256)
   if (!encode_fn()) return RCB_ERR_NO_DEVICE;
@@ -642,11 +736,14 @@ int launch_build_tc(const float* f1, const float* f2, void* const* pyr, const rc
       *m = map_l0;
       break;
     }
+    // in 4-byte words: a tile is 16 words for both element types
     cuuint64_t dims[4] = {(cuuint64_t)lay.tiles_x[l] * 16, (cuuint64_t)lay.tiles_y[l], (cuuint64_t)Q, (cuuint64_t)B};
-    cuuint64_t str[3] = {(cuuint64_t)lay.tiles_x[l] * 64, (cuuint64_t)lay.plane_stride[l] * 4,
-                         (cuuint64_t)Q * lay.plane_stride[l] * 4};
-    cuuint32_t box[4] = {32, 1, 32, 1};
-    if (!encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, pyr[l], dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B))
+    cuuint64_t str[3] = {(cuuint64_t)lay.tiles_x[l] * 64, (cuuint64_t)lay.plane_stride[l] * esize,
+                         (cuuint64_t)Q * lay.plane_stride[l] * esize};
+    const bool one_tile = f16 && l == 1;  // fp16 level 1: one 64-byte tile per query and patch
+    cuuint32_t box[4] = {(cuuint32_t)(one_tile ? 16 : 32), 1, 32, 1};
+    if (!encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, pyr[l], dims, str, box,
+                one_tile ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B))
       return RCB_ERR_INVALID_ARGUMENT;
   }
 
@@ -671,6 +768,7 @@ int launch_build_tc(const float* f1, const float* f2, void* const* pyr, const rc
     p.Hl[l] = lay.H[l]; p.Wl[l] = lay.W[l]; p.tx[l] = lay.tiles_x[l]; p.ps[l] = lay.plane_stride[l];
   }
   p.Kp = Kp;
+  p.f16 = f16 ? 1 : 0;
   p.a_pack = reinterpret_cast<const uint32_t*>(a_pack);
   p.acc_col0 = (parts * (Kp / 2) + 127) / 128 * 128;  // A occupies the first parts*Kp/2 TMEM columns
   p.nacc = (512 - p.acc_col0) / BN < MAX_ACC ? (512 - p.acc_col0) / BN : MAX_ACC;

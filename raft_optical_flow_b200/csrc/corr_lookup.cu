@@ -169,16 +169,134 @@ lookup_tma_kernel(const __grid_constant__ LookupMaps maps, PyramidDev pyr, const
   }
 }
 
+// fp16 pyramid (RCB_F16): tiles are 4 rows x 8 halfs, so a window spans 2-3 tiles in x (3-4 in y) and a tile row
+// (16 bytes) holds 8 taps; the taps are widened to fp32 on load and everything after that is the fp32 kernel with
+// one more select stage (the phase inside a tile row is 0..7).
+template <int R>
+struct TmaCfgH {
+  static constexpr int RD = 2 * R + 1;
+  static constexpr int ROWS = 2 * R + 2;
+  static constexpr int NMINX = (ROWS + 7) >> 3, NMAXX = (ROWS + 14) >> 3;
+  static constexpr int NMINY = (ROWS + 3) >> 2, NMAXY = (ROWS + 6) >> 2;
+  static constexpr int SLOT_BYTES = (NMAXX * NMAXY * 64 + 127) / 128 * 128;
+  static constexpr int SLOT16 = SLOT_BYTES / 16;
+  static constexpr int NBMAX = (RD + 3) / 4;
+  static constexpr int QT = 32, THREADS = 128;
+};
+
+template <int R>
+__global__ void __launch_bounds__(TmaCfgH<R>::THREADS, 6)
+lookup_tma_f16_kernel(const __grid_constant__ LookupMaps maps, PyramidDev pyr, const float* __restrict__ coords,
+                      float* __restrict__ out, int Q, int L) {
+  using Cfg = TmaCfgH<R>;
+  constexpr int RD = Cfg::RD, ROWS = Cfg::ROWS, NMINX = Cfg::NMINX, NMAXX = Cfg::NMAXX, NMINY = Cfg::NMINY;
+  constexpr int SLOT16 = Cfg::SLOT16, NBMAX = Cfg::NBMAX, QT = Cfg::QT;
+  __shared__ __align__(128) uint4 slots[QT * SLOT16];
+  __shared__ __align__(8) unsigned long long bars[Cfg::THREADS / 32];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int l = blockIdx.y;
+  const int b = blockIdx.z;
+  const int ql = tid >> 2, sub = tid & 3;
+  const int q = blockIdx.x * QT + ql;
+  const bool q_ok = q < Q;
+  const int Hl = l == 0 ? pyr.H[0] : l == 1 ? pyr.H[1] : l == 2 ? pyr.H[2] : pyr.H[3];
+  const int Wl = l == 0 ? pyr.W[0] : l == 1 ? pyr.W[1] : l == 2 ? pyr.W[2] : pyr.W[3];
+  float cx = -1.0e6f, cy = -1.0e6f;
+  if (q_ok) {
+    cx = __ldg(coords + (long long)(b * 2 + 0) * Q + q);
+    cy = __ldg(coords + (long long)(b * 2 + 1) * Q + q);
+  }
+  const LevelCoord lc = level_coord<R>(cx, cy, l, Hl, Wl);
+  const int ph = lc.xs & 7, py = lc.ys & 3;
+  const int nx = (ph + ROWS + 7) >> 3, ny = (py + ROWS + 3) >> 2;
+
+  const uint32_t bar = smem_u32(&bars[warp]);
+  if (lane == 0) {
+    mbar_init(bar, 8);
+    fence_barrier_init();
+  }
+  __syncwarp();
+  if (sub == 0) {
+    if (q_ok) {
+      mbar_expect_tx(bar, (uint32_t)(nx * ny * 64));
+      tma_load_3d(smem_u32(slots + ql * SLOT16), &maps.m[l * 4 + (ny - NMINY) * 2 + (nx - NMINX)], bar,
+                  (lc.xs >> 3) * 16, lc.ys >> 2, b * Q + q);
+    } else {
+      mbar_arrive(bar);
+    }
+  }
+  if (!q_ok) return;
+  const float fx = lc.fx, fy = lc.fy, gx = 1.0f - lc.fx, gy = 1.0f - lc.fy;
+  const int b0 = (RD * sub) >> 2, nb = ((RD * (sub + 1)) >> 2) - b0;  // output rows [b0, b0 + nb), nb <= NBMAX
+  float* o = out + (((long long)b * L + l) * RD * RD + b0) * Q + q;   // channel = a * RD + b
+  const long long sa = (long long)RD * Q;
+  const uint4* slot = slots + ql * SLOT16;
+  const bool ragged_w = (Wl & 7) != 0;
+  mbar_wait(bar, 0);
+
+  float hp[RD];
+#pragma unroll
+  for (int jj = 0; jj <= NBMAX; ++jj) {
+    if (jj > nb) break;
+    const int j = b0 + jj;     // window row
+    const int ya = py + j;     // row inside the fetched box
+    const bool row_ok = lc.ys + j < Hl;  // rows < 0 lie in tile rows the TMA zero-filled
+    const uint4* rowp = slot + ((ya >> 2) * nx) * 4 + (ya & 3);
+    float w[8 * NMAXX];
+#pragma unroll
+    for (int k = 0; k < NMAXX; ++k) {
+      uint4 u = make_uint4(0u, 0u, 0u, 0u);
+      if (row_ok && k < nx) u = rowp[k * 4];
+      const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+      const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+      const float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(&u.z));
+      const float2 f3 = __half22float2(*reinterpret_cast<const __half2*>(&u.w));
+      w[8 * k + 0] = f0.x; w[8 * k + 1] = f0.y; w[8 * k + 2] = f1.x; w[8 * k + 3] = f1.y;
+      w[8 * k + 4] = f2.x; w[8 * k + 5] = f2.y; w[8 * k + 6] = f3.x; w[8 * k + 7] = f3.y;
+    }
+    // t[i] = w[ph + i], ph = 0..7: three select stages
+    float v1[ROWS + 6];
+#pragma unroll
+    for (int i = 0; i < ROWS + 6; ++i) v1[i] = (ph & 1) ? w[i + 1] : w[i];
+    float v2[ROWS + 4];
+#pragma unroll
+    for (int i = 0; i < ROWS + 4; ++i) v2[i] = (ph & 2) ? v1[i + 2] : v1[i];
+    float t[ROWS];
+#pragma unroll
+    for (int i = 0; i < ROWS; ++i) t[i] = (ph & 4) ? v2[i + 4] : v2[i];
+    if (ragged_w) {
+#pragma unroll
+      for (int i = 0; i < ROWS; ++i)
+        if (lc.xs + i >= Wl) t[i] = 0.f;
+    }
+    float h[RD];
+#pragma unroll
+    for (int a = 0; a < RD; ++a) h[a] = gx * t[a] + fx * t[a + 1];
+    if (jj > 0) {
+#pragma unroll
+      for (int a = 0; a < RD; ++a) o[a * sa] = gy * hp[a] + fy * h[a];
+      o += Q;
+    }
+#pragma unroll
+    for (int a = 0; a < RD; ++a) hp[a] = h[a];
+  }
+}
+
 static int plan_init(LookupPlan* plan, const void* const* pyr, const rcb_pyramid_layout& lay, int B, int H, int W,
                      int radius) {
   if (!encode_fn()) return RCB_ERR_NO_DEVICE;
-  const int rows = 2 * radius + 2, nmin = (rows + 3) >> 2;
+  const bool f16 = lay.dtype == RCB_F16;
+  const int esize = f16 ? 2 : 4;
+  const int rows = 2 * radius + 2;
+  const int nminx = f16 ? (rows + 7) >> 3 : (rows + 3) >> 2, nminy = (rows + 3) >> 2;
   const long long planes = (long long)B * H * W;
   for (int l = 0; l < lay.levels; ++l) {
     for (int sel = 0; sel < 4; ++sel) {
-      const int nx = nmin + (sel & 1), ny = nmin + (sel >> 1);
+      const int nx = nminx + (sel & 1), ny = nminy + (sel >> 1);
+      // in 4-byte words: a 64-byte tile is 16 words for both element types
       cuuint64_t dims[3] = {(cuuint64_t)lay.tiles_x[l] * 16, (cuuint64_t)lay.tiles_y[l], (cuuint64_t)planes};
-      cuuint64_t str[2] = {(cuuint64_t)lay.tiles_x[l] * 64, (cuuint64_t)lay.plane_stride[l] * 4};
+      cuuint64_t str[2] = {(cuuint64_t)lay.tiles_x[l] * 64, (cuuint64_t)lay.plane_stride[l] * esize};
       cuuint32_t box[3] = {(cuuint32_t)nx * 16, (cuuint32_t)ny, 1};
       if (!encode(&plan->maps.m[l * 4 + sel], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, pyr[l], dims, str, box,
                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE))
@@ -207,13 +325,22 @@ static int launch_lookup_tma_r(const LookupPlan& plan, const PyramidDev& pd, con
   return launch_status();
 }
 
+template <int R>
+static int launch_lookup_tma_f16_r(const LookupPlan& plan, const PyramidDev& pd, const float* coords, float* out,
+                                   cudaStream_t s) {
+  using Cfg = TmaCfgH<R>;
+  const int Q = plan.H * plan.W;
+  dim3 grid((Q + Cfg::QT - 1) / Cfg::QT, plan.lay.levels, plan.B);
+  lookup_tma_f16_kernel<R><<<grid, Cfg::THREADS, 0, s>>>(plan.maps, pd, coords, out, Q, plan.lay.levels);
+  return launch_status();
+}
+
 size_t lookup_plan_bytes() { return sizeof(LookupPlan); }
 
 int lookup_plan_init(void* plan, size_t plan_bytes, const void* const* pyr, const rcb_pyramid_layout& lay, int B,
                      int H, int W, int radius) {
   if (!plan || plan_bytes < sizeof(LookupPlan) || (reinterpret_cast<uintptr_t>(plan) & 63))
     return RCB_ERR_INVALID_ARGUMENT;
-  if (lay.dtype != RCB_F32) return RCB_ERR_UNSUPPORTED;
   return plan_init(static_cast<LookupPlan*>(plan), pyr, lay, B, H, W, radius);
 }
 
@@ -221,6 +348,15 @@ int launch_lookup_planned(const void* plan_, const float* coords, float* out, cu
   const LookupPlan* plan = static_cast<const LookupPlan*>(plan_);
   if (!plan || (reinterpret_cast<uintptr_t>(plan_) & 63) || plan->magic != kPlanMagic) return RCB_ERR_INVALID_ARGUMENT;
   const PyramidDev pd = make_pyramid_dev(plan->ptr, plan->lay);
+  if (plan->lay.dtype == RCB_F16) {
+    switch (plan->radius) {
+      case 1: return launch_lookup_tma_f16_r<1>(*plan, pd, coords, out, s);
+      case 2: return launch_lookup_tma_f16_r<2>(*plan, pd, coords, out, s);
+      case 3: return launch_lookup_tma_f16_r<3>(*plan, pd, coords, out, s);
+      case 4: return launch_lookup_tma_f16_r<4>(*plan, pd, coords, out, s);
+      default: return RCB_ERR_UNSUPPORTED;
+    }
+  }
   switch (plan->radius) {
     case 1: return launch_lookup_tma_r<1>(*plan, pd, coords, out, s);
     case 2: return launch_lookup_tma_r<2>(*plan, pd, coords, out, s);
@@ -233,7 +369,6 @@ int launch_lookup_planned(const void* plan_, const float* coords, float* out, cu
 // Unplanned entry: encodes the tensor maps on every call (a few microseconds of host time).
 int launch_lookup(const void* const* pyr, const rcb_pyramid_layout& lay, const float* coords, float* out, int B,
                   int H, int W, int radius, cudaStream_t s) {
-  if (lay.dtype != RCB_F32) return RCB_ERR_UNSUPPORTED;
   alignas(64) LookupPlan plan;
   const int st = plan_init(&plan, pyr, lay, B, H, W, radius);
   if (st != RCB_OK) return st;

@@ -81,11 +81,13 @@ def test_corrblock_dropin_flow_matches_reference(ref, iters):
     assert want.abs().max().item() > 5.0  # a real flow field (reference CPU run: max-abs 10.6)
     orig = raft_mod.CorrBlock
     try:
-        for mode, bound in (("bf16x3", 0.01), ("fp32", 0.01), ("bf16", 0.05)):
-            raft_mod.CorrBlock = lambda f1, f2, radius=4, _m=mode: rcb.CorrBlock(f1, f2, radius=radius, mode=_m)
+        for mode, pdt, bound in (("bf16x3", "f32", 0.01), ("fp32", "f32", 0.01), ("bf16", "f32", 0.05),
+                                 ("bf16x3", "f16", 0.01), ("bf16", "f16", 0.05)):
+            raft_mod.CorrBlock = lambda f1, f2, radius=4, _m=mode, _p=pdt: rcb.CorrBlock(f1, f2, radius=radius, mode=_m,
+                                                                                           pyramid_dtype=_p)
             mean, mx = _epe(_flow(model, i1, i2, iters), want)
-            print(f"iters={iters} mode={mode}: EPE delta mean {mean:.2e} px, max {mx:.2e} px")
-            assert mean <= bound and (mode == "bf16" or mx <= 0.05), (mode, mean, mx)
+            print(f"iters={iters} mode={mode} pyramid={pdt}: EPE delta mean {mean:.2e} px, max {mx:.2e} px")
+            assert mean <= bound and (mode == "bf16" or mx <= 0.05), (mode, pdt, mean, mx)
     finally:
         raft_mod.CorrBlock = orig
 

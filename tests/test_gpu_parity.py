@@ -320,6 +320,45 @@ def test_runs_on_the_callers_stream(rcb, dev, orc):
     assert rel_err(out.cpu().numpy(), want) < TOL
 
 
+F16_TOL = 1e-3  # fp16 storage: 2^-11 relative per stored value, at most ~5e-4 of max-abs through the bilinear weights
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 23, 39, 4, 4), (1, 128, 55, 128, 4, 3), (1, 256, 46, 62, 4, 4),
+                                   (3, 32, 9, 17, 2, 1), (1, 48, 16, 33, 3, 2), (1, 256, 47, 156, 4, 4)])
+def test_fp16_pyramid_fast_mode(rcb, dev, orc, shape):
+    """pyramid_dtype="f16" (RCB_F16): same values as the fp32 pyramid up to fp16 rounding, at every level and through
+    the lookup, including plane widths that are not multiples of the 8-column fp16 tiles and out-of-plane windows."""
+    B, C, H, W, L, r = shape
+    f1n, f2n, cn = seeded(31, B, C, H, W)
+    f1, f2, c = t(f1n, dev), t(f2n, dev), t(cn, dev)
+    ref = rcb.CorrBlock(f1, f2, num_levels=L, radius=r, mode="bf16x3")
+    fast = rcb.CorrBlock(f1, f2, num_levels=L, radius=r, mode="bf16x3", pyramid_dtype="f16")
+    for a, b in zip(ref.corr_pyramid, fast.corr_pyramid):
+        assert b.dtype == torch.float16 and a.shape == b.shape
+        assert rel_err(b.float().cpu().numpy(), a.cpu().numpy()) < F16_TOL
+    want = orc.OracleCorrBlock(f1n, f2n, L, r)(cn)
+    assert rel_err(fast(c).cpu().numpy(), want) < F16_TOL
+    far = c + 1000.0  # every tap outside the plane: exact zeros
+    assert fast(far).abs().max().item() == 0.0
+    edge = c.clone()
+    edge[:, 0] = edge[:, 0] * 0.0 + (W - 1.5)  # windows hanging over the right edge
+    want_e = orc.OracleCorrBlock(f1n, f2n, L, r)(edge.cpu().numpy())
+    assert rel_err(fast(edge).cpu().numpy(), want_e) < F16_TOL
+    both = rcb.CorrBlock(f1, f2, num_levels=L, radius=r, mode="bf16", pyramid_dtype="f16")
+    assert rel_err(both(c).cpu().numpy(), want) < BF16_TOL
+
+
+def test_fp16_pyramid_is_inference_only(rcb, dev):
+    f1n, f2n, cn = seeded(32, 1, 32, 12, 16)
+    f1 = t(f1n, dev).requires_grad_(True)
+    blk = rcb.CorrBlock(f1, t(f2n, dev), num_levels=2, radius=2, pyramid_dtype="f16")
+    out = blk(t(cn, dev))
+    with pytest.raises(RuntimeError, match="unsupported"):
+        out.sum().backward()
+    with pytest.raises(RuntimeError, match="unsupported"):
+        rcb.CorrBlock(t(f1n, dev), t(f2n, dev), num_levels=2, radius=2, mode="fp32", pyramid_dtype="f16")
+
+
 def test_planned_and_unplanned_lookup_agree(rcb, dev):
     """rcb_corr_lookup encodes the TMA tensor maps per call, rcb_corr_lookup_planned reuses a caller-owned plan:
     same kernel, bit-identical output (also exercises the raw C ABI without the Python mirror)."""
