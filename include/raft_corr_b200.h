@@ -45,7 +45,8 @@ enum rcb_status {
 /* Storage type of the correlation pyramid. */
 enum rcb_dtype {
   RCB_F32 = 0, /* reference behaviour (core/corr.py keeps everything fp32) */
-  RCB_F16 = 1, /* fast mode: halves build stores and lookup reads */
+  RCB_F16 = 1, /* fast mode: halves build stores and lookup reads; tensor-core build modes and
+                  the lookup only -- the backward entry points and RCB_BUILD_FP32_SIMT return RCB_ERR_UNSUPPORTED */
 };
 
 /* Arithmetic of the all-pairs contraction (core/corr.py:121 is a true-fp32 cuBLAS SGEMM). */
