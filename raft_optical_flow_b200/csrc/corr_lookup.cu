@@ -30,6 +30,16 @@
 
 namespace rcb {
 
+// Programmatic dependent launch (griddepcontrol): a kernel launched with the programmatic-stream-serialization
+// attribute may start once every CTA of the preceding kernel in the stream has executed launch_dependents (or
+// exited) instead of when it has completed.  Only the lookup kernels execute launch_dependents, and they write
+// nothing but their own output tensor, so a following lookup can safely read the pyramid and its coordinates early;
+// it executes pdl_wait() -- which blocks until the preceding kernel has completed and flushed -- before its first
+// store, so a stream-ordered allocator that hands the same output memory to two consecutive calls stays correct.
+// Any other preceding kernel never triggers, which leaves the ordinary stream order.
+RCB_DEVINL void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+RCB_DEVINL void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 struct LevelCoord {
   int xs, ys;    // integer position of tap (0,0)
   float fx, fy;  // fractional offset shared by the whole window
@@ -105,6 +115,9 @@ lookup_tma_kernel(const __grid_constant__ LookupMaps maps, PyramidDev pyr, const
   const int ph = lc.xs & 3, py = lc.ys & 3;
   const int nx = (ph + ROWS + 3) >> 2, ny = (py + ROWS + 3) >> 2;
 
+  // Programmatic dependent launch: consecutive lookups of one GRU loop are independent (each writes its own
+  // output), so the next launch may begin its gathers while this one drains; see pdl_wait() below.
+  pdl_launch_dependents();
   const uint32_t bar = smem_u32(&bars[warp]);
   if (lane == 0) {
     mbar_init(bar, 8);
@@ -160,6 +173,7 @@ lookup_tma_kernel(const __grid_constant__ LookupMaps maps, PyramidDev pyr, const
 #pragma unroll
     for (int a = 0; a < RD; ++a) h[a] = gx * t[a] + fx * t[a + 1];
     if (jj > 0) {
+      if (jj == 1) pdl_wait();  // nothing is written before the preceding kernel of the stream has completed
 #pragma unroll
       for (int a = 0; a < RD; ++a) o[a * sa] = gy * hp[a] + fy * h[a];
       o += Q;
@@ -211,6 +225,7 @@ lookup_tma_f16_kernel(const __grid_constant__ LookupMaps maps, PyramidDev pyr, c
   const int ph = lc.xs & 7, py = lc.ys & 3;
   const int nx = (ph + ROWS + 7) >> 3, ny = (py + ROWS + 3) >> 2;
 
+  pdl_launch_dependents();
   const uint32_t bar = smem_u32(&bars[warp]);
   if (lane == 0) {
     mbar_init(bar, 8);
@@ -274,6 +289,7 @@ lookup_tma_f16_kernel(const __grid_constant__ LookupMaps maps, PyramidDev pyr, c
 #pragma unroll
     for (int a = 0; a < RD; ++a) h[a] = gx * t[a] + fx * t[a + 1];
     if (jj > 0) {
+      if (jj == 1) pdl_wait();  // nothing is written before the preceding kernel of the stream has completed
 #pragma unroll
       for (int a = 0; a < RD; ++a) o[a * sa] = gy * hp[a] + fy * h[a];
       o += Q;
@@ -314,6 +330,23 @@ static int plan_init(LookupPlan* plan, const void* const* pyr, const rcb_pyramid
   return RCB_OK;
 }
 
+static cudaLaunchConfig_t pdl_config(dim3 grid, int threads, cudaStream_t s) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3((unsigned)threads);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = s;
+  return cfg;
+}
+// RCB_LOOKUP_PDL=0 launches with ordinary stream serialization (A/B timing)
+static int pdl_attribute(cudaLaunchAttribute* attr) {
+  static const bool on = [] { const char* e = getenv("RCB_LOOKUP_PDL"); return !(e && e[0] == '0'); }();
+  if (!on) return 0;
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  return 1;
+}
+
 template <int R>
 static int launch_lookup_tma_r(const LookupPlan& plan, const PyramidDev& pd, const float* coords, float* out,
                                cudaStream_t s) {
@@ -321,7 +354,12 @@ static int launch_lookup_tma_r(const LookupPlan& plan, const PyramidDev& pd, con
   const int Q = plan.H * plan.W;
   dim3 grid((Q + Cfg::QT - 1) / Cfg::QT, plan.lay.levels, plan.B);
   static const int dbg = [] { const char* e = getenv("RCB_LOOKUP_DEBUG"); return e ? atoi(e) : 0; }();
-  lookup_tma_kernel<R><<<grid, Cfg::THREADS, 0, s>>>(plan.maps, pd, coords, out, Q, plan.lay.levels, dbg);
+  cudaLaunchConfig_t cfg = pdl_config(grid, Cfg::THREADS, s);
+  cudaLaunchAttribute attr[1];
+  cfg.numAttrs = pdl_attribute(attr);
+  cfg.attrs = attr;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, lookup_tma_kernel<R>, plan.maps, pd, coords, out, Q, (int)plan.lay.levels, dbg);
+  if (e != cudaSuccess) return (int)e;
   return launch_status();
 }
 
@@ -331,7 +369,12 @@ static int launch_lookup_tma_f16_r(const LookupPlan& plan, const PyramidDev& pd,
   using Cfg = TmaCfgH<R>;
   const int Q = plan.H * plan.W;
   dim3 grid((Q + Cfg::QT - 1) / Cfg::QT, plan.lay.levels, plan.B);
-  lookup_tma_f16_kernel<R><<<grid, Cfg::THREADS, 0, s>>>(plan.maps, pd, coords, out, Q, plan.lay.levels);
+  cudaLaunchConfig_t cfg = pdl_config(grid, Cfg::THREADS, s);
+  cudaLaunchAttribute attr[1];
+  cfg.numAttrs = pdl_attribute(attr);
+  cfg.attrs = attr;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, lookup_tma_f16_kernel<R>, plan.maps, pd, coords, out, Q, (int)plan.lay.levels);
+  if (e != cudaSuccess) return (int)e;
   return launch_status();
 }
 
