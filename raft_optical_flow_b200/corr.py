@@ -35,6 +35,8 @@ def _check_cuda(t, name):
 
 def _prep(t, name):
     _check_cuda(t, name)
+    if t.dtype is torch.float32 and not t.requires_grad and t.is_contiguous():
+        return t  # the common case (core/raft.py:181-182,216 hands over detached fp32 tensors): no torch calls
     return t.detach().float().contiguous()
 
 
@@ -155,16 +157,22 @@ class _State:
         _build(f1, f2, levels, mode, self.pyr)
         with torch.cuda.device(f1.device):
             self.plan = _cabi.LookupPlan(self.pyr.ptrs, B, H, W, levels, radius, pyr_dtype)
+        self.out_channels = levels * (2 * radius + 1) ** 2
+        self.device_index = f1.device.index if f1.device.index is not None else torch.cuda.current_device()
+        self._lookup = _cabi.lib().rcb_corr_lookup_planned
 
     def lookup(self, coords):
         B, two, H, W = coords.shape
         if (B, H, W) != (self.pyr.B, self.pyr.H, self.pyr.W) or two != 2:
             raise RuntimeError(f"coords shape {tuple(coords.shape)} does not match the feature maps")
-        rd = 2 * self.radius + 1
-        out = torch.empty((B, self.levels * rd * rd, H, W), dtype=torch.float32, device=coords.device)
-        with torch.cuda.device(coords.device):
-            _cabi.check(_cabi.lib().rcb_corr_lookup_planned(self.plan.ptr, coords.data_ptr(), out.data_ptr(),
-                                                            _stream(coords)), "rcb_corr_lookup_planned")
+        out = torch.empty((B, self.out_channels, H, W), dtype=torch.float32, device=coords.device)
+        if torch.cuda.current_device() == self.device_index:  # kernels launch on the CURRENT device
+            st = self._lookup(self.plan.ptr, coords.data_ptr(), out.data_ptr(), _stream(coords))
+        else:
+            with torch.cuda.device(coords.device):
+                st = self._lookup(self.plan.ptr, coords.data_ptr(), out.data_ptr(), _stream(coords))
+        if st != 0:
+            _cabi.check(st, "rcb_corr_lookup_planned")
         return out
 
 

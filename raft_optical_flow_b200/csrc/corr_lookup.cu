@@ -30,15 +30,11 @@
 
 namespace rcb {
 
-// Programmatic dependent launch (griddepcontrol): a kernel launched with the programmatic-stream-serialization
-// attribute may start once every CTA of the preceding kernel in the stream has executed launch_dependents (or
-// exited) instead of when it has completed.  Only the lookup kernels execute launch_dependents, and they write
-// nothing but their own output tensor, so a following lookup can safely read the pyramid and its coordinates early;
-// it executes pdl_wait() -- which blocks until the preceding kernel has completed and flushed -- before its first
-// store, so a stream-ordered allocator that hands the same output memory to two consecutive calls stays correct.
-// Any other preceding kernel never triggers, which leaves the ordinary stream order.
-RCB_DEVINL void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-RCB_DEVINL void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// Programmatic dependent launch (see tma_util.cuh): only the lookup kernels of this file execute
+// launch_dependents, and they write nothing but their own output tensor, so a following lookup can safely read the
+// pyramid and its coordinates early; it executes pdl_wait() before its first store, so a stream-ordered allocator
+// that hands the same output memory to two consecutive calls stays correct.  Any other preceding kernel never
+// triggers, which leaves the ordinary stream order.
 
 struct LevelCoord {
   int xs, ys;    // integer position of tap (0,0)

@@ -58,6 +58,13 @@ RCB_DEVINL void fence_proxy_async_smem() { asm volatile("fence.proxy.async.share
 RCB_DEVINL void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 RCB_DEVINL void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+// Programmatic dependent launch (griddepcontrol): a kernel launched with the programmatic-stream-serialization
+// attribute may start once every CTA of the preceding kernel in the stream has executed launch_dependents (or
+// exited) instead of when it has completed; pdl_wait() blocks until that preceding kernel has completed and its
+// memory operations are visible.
+RCB_DEVINL void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+RCB_DEVINL void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 RCB_DEVINL void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
