@@ -85,7 +85,10 @@ RCB_DEVINL void clamp_floor(float x, float y, int H2, int W2, int R, int& xs, in
   ys = (int)y0 - R;
 }
 
-template <int R>
+// NV > 0: channel count known at compile time (C = 128 * NV): every tap is two immediate-offset loads and 4 * NV
+// FMAs per lane, tap positions and row pointers are resolved at compile time / once per window row.
+// NV = 0: any C that is a multiple of 4 (<= 512), runtime bounds.
+template <int R, int NV>
 __global__ void __launch_bounds__(THREADS) altcorr_fwd_kernel(AltFwdParams p) {
   constexpr int RD = 2 * R + 1, T = 2 * R + 2, NT = T * T;
   constexpr int NG = (NT + 31) / 32;
@@ -125,6 +128,43 @@ __global__ void __launch_bounds__(THREADS) altcorr_fwd_kernel(AltFwdParams p) {
       qv[k] = (lane + 32 * k < C4) ? __ldg(f1q + lane + 32 * k) : make_float4(0.f, 0.f, 0.f, 0.f);
     (void)nv;
 
+    if constexpr (NV > 0) {
+      constexpr int CV = 32 * NV;  // float4 per pixel
+      const float4* __restrict__ f2v = reinterpret_cast<const float4*>(f2) + lane;
+      // validity of the window's rows / columns, one bit each (warp-uniform)
+      uint32_t rows_ok = 0, cols_ok = 0;
+#pragma unroll
+      for (int i = 0; i < T; ++i) {
+        rows_ok |= (uint32_t)(ys + i >= 0 && ys + i < H2) << i;
+        cols_ok |= (uint32_t)(xs + i >= 0 && xs + i < W2) << i;
+      }
+#pragma unroll
+      for (int g = 0; g < NG; ++g) {
+        float part[32];
+#pragma unroll
+        for (int t = 0; t < 32; ++t) {
+          const int tap = g * 32 + t;  // compile-time after unrolling
+          float s = 0.f;
+          if (tap < NT) {
+            const int iy = tap / T, ix = tap % T;
+            if (((rows_ok >> iy) & (cols_ok >> ix) & 1u) != 0u) {
+              const float4* tp = f2v + ((long long)(ys + iy) * W2 + xs) * CV + ix * CV;
+#pragma unroll
+              for (int k = 0; k < NV; ++k) {
+                const float4 v = __ldg(tp + 32 * k);
+                s = fmaf(qv[k].x, v.x, s);
+                s = fmaf(qv[k].y, v.y, s);
+                s = fmaf(qv[k].z, v.z, s);
+                s = fmaf(qv[k].w, v.w, s);
+              }
+            }
+          }
+          part[t] = s;
+        }
+        const float d = transpose_reduce32(part, lane);
+        s_dot[warp][g * 32 + lane] = d;
+      }
+    } else
 #pragma unroll 1
     for (int g = 0; g < NG; ++g) {
       float part[32];
@@ -178,7 +218,11 @@ __global__ void __launch_bounds__(THREADS) altcorr_fwd_kernel(AltFwdParams p) {
 template <int R>
 static int launch_fwd_r(const AltFwdParams& p, int B, cudaStream_t s) {
   dim3 grid((p.Q + QT - 1) / QT, p.slots, B);
-  altcorr_fwd_kernel<R><<<grid, THREADS, 0, s>>>(p);
+  switch (p.C) {
+    case 128: altcorr_fwd_kernel<R, 1><<<grid, THREADS, 0, s>>>(p); break;  // RAFT-small
+    case 256: altcorr_fwd_kernel<R, 2><<<grid, THREADS, 0, s>>>(p); break;  // RAFT-full
+    default: altcorr_fwd_kernel<R, 0><<<grid, THREADS, 0, s>>>(p); break;
+  }
   return launch_status();
 }
 

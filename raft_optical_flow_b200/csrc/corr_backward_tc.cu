@@ -297,7 +297,8 @@ int launch_contract_backward_tc(const float* f1, const float* f2, const float* d
   if (nstage > 4) nstage = 4;
   if (nstage < 2) return RCB_ERR_UNSUPPORTED;
   const int smem_total = nstage * stage_bytes + 1024;
-  static const cudaError_t attr =
+  // per launch, not once per process: the attribute belongs to the current device (nn.DataParallel drives several)
+  const cudaError_t attr =
       cudaFuncSetAttribute(gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (attr != cudaSuccess) return (int)attr;
   for (int g = 0; g < 2; ++g) {
