@@ -401,3 +401,29 @@ def test_cta_pair_build_matches_single_cta(dev):
             outs.append(torch.load(f.name))
     for a, b in zip(*outs):
         assert torch.equal(a, b)  # same products in the same order: bit-identical
+
+
+def test_dependent_launches_keep_results_and_stream_order(rcb, dev):
+    """Consecutive lookups are launched as programmatic dependents (the next one gathers while the previous one
+    drains, its stores wait).  Back-to-back launches without any synchronisation in between must give the results of
+    the same calls made one at a time, also when the allocator recycles the output memory of earlier calls."""
+    f1n, f2n, _ = seeded(41, 2, 64, 31, 45)
+    blk = rcb.CorrBlock(t(f1n, dev), t(f2n, dev), num_levels=4, radius=4)
+    cs = [t(seeded(50 + i, 2, 64, 31, 45)[2], dev) for i in range(8)]
+    want = []
+    for c in cs:  # one at a time, fully synchronised
+        want.append(blk(c).clone())
+        torch.cuda.synchronize()
+    for rep in range(10):
+        outs = [blk(c) for c in cs]  # 8 launches back to back, all outputs alive
+        torch.cuda.synchronize()
+        for o, w in zip(outs, want):
+            assert torch.equal(o, w)
+        del outs
+        ptrs, out, prev = set(), None, None
+        for i in range(64):  # rebinding frees the block before last: it is handed to the next call
+            prev, out = out, blk(cs[i % 8])
+            ptrs.add(out.data_ptr())
+        torch.cuda.synchronize()
+        assert torch.equal(out, want[63 % 8]) and torch.equal(prev, want[62 % 8])
+        assert len(ptrs) <= 4  # the allocator did recycle output memory
