@@ -104,37 +104,53 @@ __host__ __device__ constexpr uint32_t make_idesc(int ncta) {
 
 // ---- operand packing -----------------------------------------------------------------------
 // in  [2 maps][B][C][Q] fp32 (two separate base pointers);  out [map][part][B][Q][Kp] bf16, zero padded to Kp.
+// CTA = 64 channels x 64 queries: coalesced 8-byte loads along q into a padded fp32 tile, then every thread turns
+// 8 channels of one query into one 16-byte store per part (8 lanes cover the 128 bytes of a query's k-block).
 __global__ void __launch_bounds__(256)
 pack_operands_kernel(const float* __restrict__ f1, const float* __restrict__ f2, __nv_bfloat16* __restrict__ out,
                      int B, int C, int Q, int Kp, int parts) {
-  __shared__ float tile[64][33];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  __shared__ float tile[64][65];  // odd pitch: the column reads below are at most 2-way bank-conflicted
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int map = blockIdx.z / B, b = blockIdx.z % B;
   const float* in = (map == 0 ? f1 : f2) + (long long)b * C * Q;
-  const int q0 = blockIdx.x * 32, c0 = blockIdx.y * 64;
-  for (int c = ty; c < 64; c += 8) {
-    const int cc = c0 + c, q = q0 + tx;
-    tile[c][tx] = (cc < C && q < Q) ? __ldg(in + (long long)cc * Q + q) : 0.f;
+  const int q0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
+  const bool even_q = (Q & 1) == 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = warp * 8 + i, cc = c0 + c, q = q0 + 2 * lane;
+    float2 v = make_float2(0.f, 0.f);
+    if (cc < C) {
+      const float* src = in + (long long)cc * Q + q;
+      if (even_q && q + 1 < Q) {
+        v = __ldg(reinterpret_cast<const float2*>(src));  // rows start 8-byte aligned when Q is even
+      } else {
+        if (q < Q) v.x = __ldg(src);
+        if (q + 1 < Q) v.y = __ldg(src + 1);
+      }
+    }
+    tile[c][2 * lane] = v.x;
+    tile[c][2 * lane + 1] = v.y;
   }
   __syncthreads();
   const long long part_stride = (long long)B * Q * Kp;
   __nv_bfloat16* o = out + (long long)map * parts * part_stride + (long long)b * Q * Kp;
-  for (int i = ty; i < 32; i += 8) {
-    const int q = q0 + i;
+  const int cg = lane & 7;  // group of 8 channels
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int ql = warp * 8 + i * 4 + (lane >> 3), q = q0 + ql;
     if (q >= Q) continue;
-    const float x0 = tile[2 * tx][i], x1 = tile[2 * tx + 1][i];
-    const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
-    __nv_bfloat162 hi;
-    hi.x = h0;
-    hi.y = h1;
-    __nv_bfloat162* dst = reinterpret_cast<__nv_bfloat162*>(o + (long long)q * Kp + c0) + tx;
-    *dst = hi;
-    if (parts > 1) {
-      __nv_bfloat162 lo;
-      lo.x = __float2bfloat16_rn(x0 - __bfloat162float(h0));
-      lo.y = __float2bfloat16_rn(x1 - __bfloat162float(h1));
-      *reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<__nv_bfloat16*>(dst) + part_stride) = lo;
+    __nv_bfloat162 hi[4], lo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float x0 = tile[8 * cg + 2 * j][ql], x1 = tile[8 * cg + 2 * j + 1][ql];
+      const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
+      hi[j] = __halves2bfloat162(h0, h1);
+      lo[j] = __halves2bfloat162(__float2bfloat16_rn(x0 - __bfloat162float(h0)),
+                                 __float2bfloat16_rn(x1 - __bfloat162float(h1)));
     }
+    __nv_bfloat16* dst = o + (long long)q * Kp + c0 + 8 * cg;
+    *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(hi);
+    if (parts > 1) *reinterpret_cast<uint4*>(dst + part_stride) = *reinterpret_cast<const uint4*>(lo);
   }
 }
 
@@ -712,7 +728,7 @@ int launch_build_tc(const float* f1, const float* f2, void* const* pyr, const rc
   // 1. pack: fp32 NCHW -> bf16 hi/lo, K-major
   __nv_bfloat16* packed = static_cast<__nv_bfloat16*>(ws);
   {
-    dim3 grid((Q + 31) / 32, Kp / 64, 2 * B);
+    dim3 grid((Q + 63) / 64, Kp / 64, 2 * B);
     pack_operands_kernel<<<grid, 256, 0, s>>>(f1, f2, packed, B, C, Q, Kp, parts);
     int st = launch_status();
     if (st != RCB_OK) return st;
