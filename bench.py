@@ -143,6 +143,8 @@ def run_reference(args, cfg):
         return 0
     B, C, H, W, r, L, iters, desc = cfg
     from oracle import oracle as orc
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; the reference arm is meant to use every host core it can
+    orc.set_num_threads(len(os.sched_getaffinity(0)))
     cores = orc.num_threads()
     sample_pairs = B  # the whole batch: a step is ~1-2 s of CPU work on 8 cores
     for _ in range(args.warmup):
@@ -351,6 +353,7 @@ def run_ours(args, cfg):
         line["fast_mode"] = fast
     if world == 1 and not args.no_cpu_baseline:
         from oracle import oracle as orc
+        orc.set_num_threads(len(os.sched_getaffinity(0)))
         cores = orc.num_threads()
         cpu_reference_step(1, C, H, W, r, L, 2, SEED)  # warm the OpenMP pool / page in the library
         dt, tb, tl = cpu_reference_step(B, C, H, W, r, L, iters, SEED)
