@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define RCB_ABI_VERSION 4
+#define RCB_ABI_VERSION 5
 #define RCB_MAX_LEVELS 4 /* core/raft.py:46-53 fixes corr_levels = 4 */
 #define RCB_MAX_RADIUS 4 /* core/raft.py:47,53: radius 3 (small) / 4 (full) */
 
@@ -168,6 +168,17 @@ RCB_API int rcb_altcorr_prepare(const float* fmap1, const float* fmap2, float* f
 RCB_API int rcb_altcorr_pyramid_forward(const float* fmap1_nhwc, const float* const* fmap2_nhwc, const float* coords,
                                 float* out, int B, int C, int H, int W, int levels, int radius, float scale,
                                 rcb_stream_t stream);
+
+/* ---- next row: convex upsampling of the flow -------------------------------
+ * Replaces RAFT.upsample_flow (core/raft.py:112-142: view, softmax over the 9 neighbours, F.unfold(8*flow, 3x3,
+ * padding=1), weighted sum, permute, reshape), called once per GRU iteration (core/raft.py:240).
+ *   flow [N, 2, H, W], mask [N, 576, H, W] (channel = k*64 + i*8 + j)  ->  out [N, 2, 8H, 8W]
+ * Backward: d flow [N, 2, H, W] and d mask [N, 576, H, W] from d out; `workspace` holds N*2*9*H*W floats. */
+RCB_API int rcb_upsample_flow(const float* flow, const float* mask, float* out, int N, int H, int W, rcb_stream_t stream);
+RCB_API size_t rcb_upsample_flow_backward_workspace_bytes(int N, int H, int W);
+RCB_API int rcb_upsample_flow_backward(const float* flow, const float* mask, const float* grad_out, float* dflow,
+                               float* dmask, void* workspace, size_t workspace_bytes, int N, int H, int W,
+                               rcb_stream_t stream);
 
 #ifdef __cplusplus
 }

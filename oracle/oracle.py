@@ -210,3 +210,48 @@ class OracleAlternateCorrBlock:
             outs.append(altcorr_forward(f1, f2, ci, self.radius)[:, 0])  # corr.py:190-191
         corr = np.stack(outs, axis=1).reshape(B, -1, H, W)  # corr.py:194-195
         return corr / np.sqrt(np.float32(dim))  # corr.py:198
+
+
+# ---- next row: convex upsampling ----------------------------------------------------------
+def _unfold3x3(x8):
+    """F.unfold(x, [3, 3], padding=1) of core/raft.py:132 as an array [N, 2, 9, H, W]: neighbour k = ky*3 + kx is
+    x[.., h + ky - 1, w + kx - 1], zero outside."""
+    N, C, H, W = x8.shape
+    pad = np.zeros((N, C, H + 2, W + 2), dtype=x8.dtype)
+    pad[:, :, 1:-1, 1:-1] = x8
+    return np.stack([pad[:, :, ky:ky + H, kx:kx + W] for ky in range(3) for kx in range(3)], axis=2)
+
+
+def _softmax9(mask):
+    N, _, H, W = mask.shape
+    m = mask.reshape(N, 9, 8, 8, H, W).astype(np.float64)  # core/raft.py:128: view(N, 1, 9, 8, 8, H, W)
+    m = np.exp(m - m.max(axis=1, keepdims=True))
+    return m / m.sum(axis=1, keepdims=True)                # core/raft.py:130: softmax over the 9 neighbours
+
+
+def upsample_flow(flow, mask):
+    """RAFT.upsample_flow (reference core/raft.py:112-142) in numpy (float64 accumulation):
+    flow [N,2,H,W], mask [N,576,H,W] -> [N,2,8H,8W]."""
+    N, _, H, W = flow.shape
+    p = _softmax9(mask)                                     # [N, 9, 8, 8, H, W]
+    nb = _unfold3x3(8.0 * flow.astype(np.float64))          # [N, 2, 9, H, W]   (core/raft.py:132-133)
+    up = np.einsum("nkijhw,nckhw->ncijhw", p, nb)           # core/raft.py:136: sum(mask * up_flow, dim=2)
+    return up.transpose(0, 1, 4, 2, 5, 3).reshape(N, 2, 8 * H, 8 * W).astype(np.float32)  # core/raft.py:138-140
+
+
+def upsample_flow_backward(flow, mask, grad_out):
+    """Gradients of upsample_flow w.r.t. flow and mask for the cotangent grad_out [N,2,8H,8W] (what autograd yields
+    for core/raft.py:112-142)."""
+    N, _, H, W = flow.shape
+    p = _softmax9(mask)
+    nb = _unfold3x3(8.0 * flow.astype(np.float64))
+    g = grad_out.astype(np.float64).reshape(N, 2, H, 8, W, 8).transpose(0, 1, 3, 5, 2, 4)  # [N, 2, i, j, H, W]
+    gn = np.einsum("ncijhw,nckhw->nkijhw", g, nb)           # d out / d p_k contracted with the cotangent
+    dmask = p * (gn - (p * gn).sum(axis=1, keepdims=True))  # softmax Jacobian
+    dnb = np.einsum("nkijhw,ncijhw->nckhw", p, g)           # [N, 2, 9, H, W]
+    dpad = np.zeros((N, 2, H + 2, W + 2))
+    for ky in range(3):
+        for kx in range(3):
+            dpad[:, :, ky:ky + H, kx:kx + W] += dnb[:, :, ky * 3 + kx]
+    dflow = 8.0 * dpad[:, :, 1:-1, 1:-1]
+    return dflow.astype(np.float32), dmask.reshape(N, 576, H, W).astype(np.float32)

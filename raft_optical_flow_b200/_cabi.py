@@ -9,7 +9,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libraftcorr_b200.so")
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 MAX_LEVELS = 4
 MAX_RADIUS = 4
 
@@ -57,6 +57,9 @@ SIGNATURES = {
     "rcb_altcorr_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "rcb_altcorr_prepare": (_i, [_vp, _vp, _vp, ctypes.POINTER(_vp), _i, _i, _i, _i, _i, _vp]),
     "rcb_altcorr_pyramid_forward": (_i, [_vp, ctypes.POINTER(_vp), _vp, _vp, _i, _i, _i, _i, _i, _i, ctypes.c_float, _vp]),
+    "rcb_upsample_flow": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
+    "rcb_upsample_flow_backward_workspace_bytes": (ctypes.c_size_t, [_i, _i, _i]),
+    "rcb_upsample_flow_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_size_t, _i, _i, _i, _vp]),
 }
 
 _lib = None

@@ -179,4 +179,25 @@ int rcb_altcorr_pyramid_forward(const float* fmap1_nhwc, const float* const* fma
                                         reinterpret_cast<cudaStream_t>(stream));
 }
 
+int rcb_upsample_flow(const float* flow, const float* mask, float* out, int N, int H, int W, rcb_stream_t stream) {
+  if (!flow || !mask || !out || N <= 0 || H <= 0 || W <= 0) return RCB_ERR_INVALID_ARGUMENT;
+  if (!aligned16(out)) return RCB_ERR_INVALID_ARGUMENT;
+  return launch_upsample_flow(flow, mask, out, N, H, W, reinterpret_cast<cudaStream_t>(stream));
+}
+
+size_t rcb_upsample_flow_backward_workspace_bytes(int N, int H, int W) {
+  if (N <= 0 || H <= 0 || W <= 0) return 0;
+  return (size_t)N * 2 * 9 * H * W * sizeof(float);
+}
+
+int rcb_upsample_flow_backward(const float* flow, const float* mask, const float* grad_out, float* dflow,
+                               float* dmask, void* workspace, size_t workspace_bytes, int N, int H, int W,
+                               rcb_stream_t stream) {
+  if (!flow || !mask || !grad_out || !dflow || !dmask || N <= 0 || H <= 0 || W <= 0) return RCB_ERR_INVALID_ARGUMENT;
+  if (!aligned16(grad_out)) return RCB_ERR_INVALID_ARGUMENT;
+  if (!workspace || workspace_bytes < rcb_upsample_flow_backward_workspace_bytes(N, H, W)) return RCB_ERR_WORKSPACE;
+  return launch_upsample_flow_backward(flow, mask, grad_out, dflow, dmask, static_cast<float*>(workspace), N, H, W,
+                                       reinterpret_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

@@ -131,6 +131,9 @@ int launch_altcorr_forward(const float* f1, const float* f2, const float* coords
 int launch_altcorr_backward(const float* f1, const float* f2, const float* coords, const float* cg, float* g1,
                             float* g2, float* gc, int B, int N, int H1, int W1, int H2, int W2, int C, int r,
                             int true_cg, cudaStream_t s);
+int launch_upsample_flow(const float* flow, const float* mask, float* out, int N, int H, int W, cudaStream_t s);
+int launch_upsample_flow_backward(const float* flow, const float* mask, const float* gout, float* dflow, float* dmask,
+                                  float* workspace, int N, int H, int W, cudaStream_t s);
 int launch_altcorr_prepare(const float* f1, const float* f2, float* f1n, float* const* f2n, int B, int C, int H,
                            int W, int levels, cudaStream_t s);
 int launch_altcorr_pyramid_forward(const float* f1n, const float* const* f2n, const float* coords, float* out,

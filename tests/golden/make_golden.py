@@ -204,12 +204,27 @@ def case_raft_small_crop():
          flow_lo=flow_lo.numpy())
 
 
+def case_upsample_flow():
+    """Convex upsampling (next row of the scope table): RAFT.upsample_flow (core/raft.py:112-142) on seeded flow and
+    mask tensors of an odd size, with the gradients autograd yields for a seeded cotangent."""
+    import raft as raft_mod
+    N, H, W, seed = 2, 7, 11, 77
+    r = rs(seed)
+    flow = torch.from_numpy((3.0 * r.standard_normal((N, 2, H, W))).astype(np.float32)).requires_grad_(True)
+    mask = torch.from_numpy((2.0 * r.standard_normal((N, 576, H, W))).astype(np.float32)).requires_grad_(True)
+    out = raft_mod.RAFT.upsample_flow(None, flow, mask)  # the method does not use self
+    g = cotangent(seed, tuple(out.shape))
+    out.backward(torch.from_numpy(g))
+    save("upsample_flow", meta=np.array([N, H, W, seed]), flow=flow.detach().numpy(), mask=mask.detach().numpy(),
+         out=out.detach().numpy(), dflow=flow.grad.numpy(), dmask=mask.grad.numpy())
+
+
 if __name__ == "__main__":
     p = argparse.ArgumentParser()
     p.add_argument("--only", default=None)
     a = p.parse_args()
     cases = [case_odd, case_full, case_small, case_edges, case_known_answers, case_alt_formulation,
-             case_raft_small_crop]
+             case_raft_small_crop, case_upsample_flow]
     for c in cases:
         if a.only is None or a.only in c.__name__:
             c()

@@ -92,6 +92,28 @@ def test_corrblock_dropin_flow_matches_reference(ref, iters):
         raft_mod.CorrBlock = orig
 
 
+def test_patch_raft_with_fused_upsampling_matches_reference(ref):
+    """patch_raft: correlation blocks + the fused convex upsampling (RAFT.upsample_flow, core/raft.py:112-142) in the
+    unmodified reference model; inference flow and the training-mode list of upsampled predictions."""
+    import raft_optical_flow_b200 as rcb
+    d, raft_mod, ref_corr, InputPadder = ref
+    model, i1, i2 = _load(d, raft_mod, InputPadder, alternate=False)
+    want = _flow(model, i1, i2, 12)
+    with torch.no_grad():
+        want_seq = model(i1, i2, iters=4)
+    old = rcb.patch_raft(raft_mod)
+    try:
+        mean, mx = _epe(_flow(model, i1, i2, 12), want)
+        print(f"patch_raft: EPE delta mean {mean:.2e} px, max {mx:.2e} px")
+        assert mean <= 0.01 and mx <= 0.05
+        with torch.no_grad():
+            got_seq = model(i1, i2, iters=4)
+        for a, b in zip(got_seq, want_seq):
+            assert _epe(a, b)[0] <= 0.01
+    finally:
+        raft_mod.CorrBlock, raft_mod.AlternateCorrBlock, raft_mod.RAFT.upsample_flow = old
+
+
 def test_alternate_corr_dropin_flow_matches_reference(ref):
     """--alternate_corr: (a) our AlternateCorrBlock patched in; (b) the reference's own AlternateCorrBlock running
     on top of our `alt_cuda_corr` module (extension-level drop-in, core/corr.py:6,190)."""

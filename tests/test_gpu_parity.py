@@ -427,3 +427,33 @@ def test_dependent_launches_keep_results_and_stream_order(rcb, dev):
         torch.cuda.synchronize()
         assert torch.equal(out, want[63 % 8]) and torch.equal(prev, want[62 % 8])
         assert len(ptrs) <= 4  # the allocator did recycle output memory
+
+
+# ---------------------------------------------------------------------------------------------
+# next row of the scope table: convex upsampling (RAFT.upsample_flow, core/raft.py:112-142)
+# ---------------------------------------------------------------------------------------------
+def test_upsample_flow_golden_forward_and_backward(rcb, dev):
+    g = load_golden("upsample_flow")
+    N, H, W, seed = [int(v) for v in g["meta"]]
+    flow = t(g["flow"], dev).requires_grad_(True)
+    mask = t(g["mask"], dev).requires_grad_(True)
+    out = rcb.upsample_flow(flow, mask)
+    assert tuple(out.shape) == (N, 2, 8 * H, 8 * W)
+    assert rel_err(out.detach().cpu().numpy(), g["out"]) < TOL
+    out.backward(t(cotangent(seed, g["out"].shape), dev))
+    assert rel_err(flow.grad.cpu().numpy(), g["dflow"]) < GRAD_TOL
+    assert rel_err(mask.grad.cpu().numpy(), g["dmask"]) < GRAD_TOL
+
+
+@pytest.mark.parametrize("dims", [(1, 55, 128), (3, 46, 62), (2, 1, 1), (1, 5, 33)])
+def test_upsample_flow_vs_oracle(rcb, dev, orc, dims):
+    N, H, W = dims
+    rs = np.random.RandomState(5)
+    flow = (4.0 * rs.standard_normal((N, 2, H, W))).astype(np.float32)
+    mask = (3.0 * rs.standard_normal((N, 576, H, W))).astype(np.float32)
+    got = rcb.upsample_flow(t(flow, dev), t(mask, dev)).cpu().numpy()
+    assert rel_err(got, orc.upsample_flow(flow, mask)) < TOL
+    # uniform logits: every fine pixel is the mean of its 3x3 neighbourhood of 8*flow (zero padded)
+    flat = rcb.upsample_flow(t(flow, dev), torch.zeros(N, 576, H, W, device=dev)).cpu().numpy()
+    assert rel_err(flat, orc.upsample_flow(flow, np.zeros_like(mask))) < TOL
+    assert np.abs(flat[:, :, ::8, ::8] - flat[:, :, 7::8, 7::8]).max() < 1e-5  # constant inside a coarse cell

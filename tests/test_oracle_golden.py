@@ -166,3 +166,14 @@ def test_oracle_vs_live_reference_midsize():
         assert rel_err(blk.corr_pyramid[i], ref.corr_pyramid[i].numpy()[:, 0]) < FWD_TOL
     assert rel_err(blk(coords), want) < FWD_TOL
     assert rel_err(orc.OracleAlternateCorrBlock(f1, f2, L, r)(coords), want) < 2e-5
+
+
+def test_upsample_flow_oracle_matches_reference_golden():
+    """oracle.upsample_flow / upsample_flow_backward vs RAFT.upsample_flow and its autograd (core/raft.py:112-142)."""
+    from oracle import oracle as orc
+    g = load_golden("upsample_flow")
+    N, H, W, seed = [int(v) for v in g["meta"]]
+    assert rel_err(orc.upsample_flow(g["flow"], g["mask"]), g["out"]) < 1e-5
+    dflow, dmask = orc.upsample_flow_backward(g["flow"], g["mask"], cotangent(seed, g["out"].shape))
+    assert rel_err(dflow, g["dflow"]) < 1e-4
+    assert rel_err(dmask, g["dmask"]) < 1e-4
