@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define RCB_ABI_VERSION 5
+#define RCB_ABI_VERSION 6
 #define RCB_MAX_LEVELS 4 /* core/raft.py:46-53 fixes corr_levels = 4 */
 #define RCB_MAX_RADIUS 4 /* core/raft.py:47,53: radius 3 (small) / 4 (full) */
 
@@ -179,6 +179,23 @@ RCB_API size_t rcb_upsample_flow_backward_workspace_bytes(int N, int H, int W);
 RCB_API int rcb_upsample_flow_backward(const float* flow, const float* mask, const float* grad_out, float* dflow,
                                float* dmask, void* workspace, size_t workspace_bytes, int N, int H, int W,
                                rcb_stream_t stream);
+
+/* ---- lookup fused with the motion encoder's first layer ----------------------------------
+ * Replaces the pair  corr = corr_fn(coords1)  (core/raft.py:219)  ->  cor = F.relu(self.convc1(corr))
+ * (core/update.py:154 SmallMotionEncoder, :202 BasicMotionEncoder; convc1 = Conv2d(levels*(2r+1)^2, cout, 1),
+ * core/update.py:136,182): out[b, n, y, x] = act(sum_k corr[b, k, y, x] * weight[n, k] + bias[n]) without ever
+ * materialising corr.  fp16 operands on the tensor cores, fp32 accumulate (same class as the TF32 convolution the
+ * reference gets from cuDNN by default): within 1e-3 of max-abs of the fp32 result.  fp32 pyramids, radius 3 or 4,
+ * cout a multiple of 16 in 16..256; anything else returns RCB_ERR_UNSUPPORTED (0 bytes from the size query).
+ *   rcb_corr_convc1_pack   weight [cout][levels*(2r+1)^2] fp32 (the Conv2d weight, contiguous) -> the kernel's
+ *                          K-permuted, zero-padded fp16 operand; once per set of weights.  wpack: 128-byte aligned,
+ *                          rcb_corr_convc1_pack_bytes() bytes.
+ *   rcb_corr_lookup_convc1 plan: a lookup plan of the pyramid (rcb_corr_lookup_plan_init); bias may be NULL;
+ *                          relu != 0 applies max(x, 0); out [B][cout][H][W] fp32. */
+RCB_API size_t rcb_corr_convc1_pack_bytes(int cout, int levels, int radius);
+RCB_API int rcb_corr_convc1_pack(const float* weight, void* wpack, int cout, int levels, int radius, rcb_stream_t stream);
+RCB_API int rcb_corr_lookup_convc1(const void* plan, const float* coords, const void* wpack, const float* bias,
+                                   float* out, int cout, int relu, rcb_stream_t stream);
 
 #ifdef __cplusplus
 }

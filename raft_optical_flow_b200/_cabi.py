@@ -9,7 +9,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libraftcorr_b200.so")
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 MAX_LEVELS = 4
 MAX_RADIUS = 4
 
@@ -60,6 +60,9 @@ SIGNATURES = {
     "rcb_upsample_flow": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "rcb_upsample_flow_backward_workspace_bytes": (ctypes.c_size_t, [_i, _i, _i]),
     "rcb_upsample_flow_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_size_t, _i, _i, _i, _vp]),
+    "rcb_corr_convc1_pack_bytes": (ctypes.c_size_t, [_i, _i, _i]),
+    "rcb_corr_convc1_pack": (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    "rcb_corr_lookup_convc1": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
 }
 
 _lib = None

@@ -19,7 +19,7 @@ import torch.nn.functional as F
 
 from . import _cabi
 
-__all__ = ["CorrBlock", "AlternateCorrBlock"]
+__all__ = ["CorrBlock", "AlternateCorrBlock", "PackedConvC1"]
 
 DEFAULT_MODE = os.environ.get("RAFT_CORR_MODE", "bf16x3")
 
@@ -176,6 +176,30 @@ class _State:
         return out
 
 
+class PackedConvC1:
+    """Weights of the motion encoder's first layer (``convc1``, reference core/update.py:136,182) in the operand
+    layout of the fused lookup kernel (``rcb_corr_convc1_pack``).  Pack once per set of weights, reuse every
+    iteration: ``block.lookup_conv(coords, packed)``."""
+
+    def __init__(self, weight, bias, num_levels=4, radius=4):
+        _check_cuda(weight, "weight")
+        cout = weight.shape[0]
+        cin = num_levels * (2 * radius + 1) ** 2
+        w = weight.detach().float().reshape(cout, -1).contiguous()
+        if w.shape[1] != cin:
+            raise RuntimeError(f"convc1 weight has {w.shape[1]} input channels, the lookup produces {cin}")
+        lib = _cabi.lib()
+        n = lib.rcb_corr_convc1_pack_bytes(cout, num_levels, radius)
+        if n == 0:
+            raise RuntimeError("fused lookup + convc1 supports radius 3/4 and 16..256 output channels in steps of 16")
+        self.cout, self.num_levels, self.radius = cout, num_levels, radius
+        self.wpack = torch.empty(n, dtype=torch.uint8, device=weight.device)
+        self.bias = None if bias is None else bias.detach().float().contiguous()
+        with torch.cuda.device(weight.device):
+            _cabi.check(lib.rcb_corr_convc1_pack(w.data_ptr(), self.wpack.data_ptr(), cout, num_levels, radius,
+                                                 _stream(weight)), "rcb_corr_convc1_pack")
+
+
 class CorrBlock:
     """All-pairs correlation pyramid with per-iteration window lookup (reference core/corr.py:12-94)."""
 
@@ -204,6 +228,27 @@ class CorrBlock:
         if torch.is_grad_enabled() and (self._token is not None or coords.requires_grad):
             return _LookupFn.apply(coords, self._token, self._state)
         return self._state.lookup(_prep(coords, "coords"))
+
+    def lookup_conv(self, coords, packed, relu=True):
+        """relu(convc1(self(coords))) in one kernel (reference core/raft.py:219 + core/update.py:154,202) without
+        materialising the correlation tensor; ``packed`` is a PackedConvC1.  Inference only (no autograd), fp32
+        pyramids; fp16 tensor-core operands with fp32 accumulation.  Returns [N, cout, H, W] fp32."""
+        st = self._state
+        if st.pyr.dtype != _cabi.F32:
+            raise RuntimeError("lookup_conv needs an fp32 pyramid")
+        if (packed.num_levels, packed.radius) != (self.num_levels, self.radius):
+            raise RuntimeError("PackedConvC1 was packed for a different num_levels / radius")
+        c = _prep(coords, "coords")
+        B, two, H, W = c.shape
+        if (B, H, W) != (st.pyr.B, st.pyr.H, st.pyr.W) or two != 2:
+            raise RuntimeError(f"coords shape {tuple(c.shape)} does not match the feature maps")
+        out = torch.empty((B, packed.cout, H, W), dtype=torch.float32, device=c.device)
+        with torch.cuda.device(c.device):
+            _cabi.check(_cabi.lib().rcb_corr_lookup_convc1(
+                st.plan.ptr, c.data_ptr(), packed.wpack.data_ptr(),
+                None if packed.bias is None else packed.bias.data_ptr(), out.data_ptr(), packed.cout, int(relu),
+                _stream(c)), "rcb_corr_lookup_convc1")
+        return out
 
     @staticmethod
     def corr(fmap1, fmap2, mode=None):

@@ -200,4 +200,15 @@ int rcb_upsample_flow_backward(const float* flow, const float* mask, const float
                                        reinterpret_cast<cudaStream_t>(stream));
 }
 
+size_t rcb_corr_convc1_pack_bytes(int cout, int levels, int radius) { return convc1_pack_bytes(cout, levels, radius); }
+
+int rcb_corr_convc1_pack(const float* weight, void* wpack, int cout, int levels, int radius, rcb_stream_t stream) {
+  return launch_convc1_pack(weight, wpack, cout, levels, radius, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int rcb_corr_lookup_convc1(const void* plan, const float* coords, const void* wpack, const float* bias, float* out,
+                           int cout, int relu, rcb_stream_t stream) {
+  return launch_lookup_convc1(plan, coords, wpack, bias, out, cout, relu, reinterpret_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

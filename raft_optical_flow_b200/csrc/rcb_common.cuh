@@ -134,6 +134,10 @@ int launch_altcorr_backward(const float* f1, const float* f2, const float* coord
 int launch_upsample_flow(const float* flow, const float* mask, float* out, int N, int H, int W, cudaStream_t s);
 int launch_upsample_flow_backward(const float* flow, const float* mask, const float* gout, float* dflow, float* dmask,
                                   float* workspace, int N, int H, int W, cudaStream_t s);
+size_t convc1_pack_bytes(int cout, int levels, int radius);
+int launch_convc1_pack(const float* weight, void* wpack, int cout, int levels, int radius, cudaStream_t s);
+int launch_lookup_convc1(const void* plan, const float* coords, const void* wpack, const float* bias, float* out,
+                         int cout, int relu, cudaStream_t s);
 int launch_altcorr_prepare(const float* f1, const float* f2, float* f1n, float* const* f2n, int B, int C, int H,
                            int W, int levels, cudaStream_t s);
 int launch_altcorr_pyramid_forward(const float* f1n, const float* const* f2n, const float* coords, float* out,

@@ -147,5 +147,10 @@ __host__ __device__ constexpr uint32_t make_idesc_mn(int m, int n) {
          ((uint32_t)(m >> 4) << 24);
 }
 
+// the same with fp16 x fp16 operands (formats 0), fp32 accumulate
+__host__ __device__ constexpr uint32_t make_idesc_f16_mn(int m, int n) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
 }  // namespace tc
 }  // namespace rcb
