@@ -255,3 +255,16 @@ def upsample_flow_backward(flow, mask, grad_out):
             dpad[:, :, ky:ky + H, kx:kx + W] += dnb[:, :, ky * 3 + kx]
     dflow = 8.0 * dpad[:, :, 1:-1, 1:-1]
     return dflow.astype(np.float32), dmask.reshape(N, 576, H, W).astype(np.float32)
+
+
+def convc1_relu(corr, weight, bias=None, relu=True):
+    """First layer of the motion encoder on the lookup output: relu(convc1(corr)) with convc1 a 1x1 convolution
+    (reference core/update.py:136,154 SmallMotionEncoder, :182,202 BasicMotionEncoder), float64 accumulation.
+    corr [N,K,H,W], weight [Cout,K] or [Cout,K,1,1], bias [Cout] -> [N,Cout,H,W]."""
+    w = np.asarray(weight, dtype=np.float64).reshape(weight.shape[0], -1)
+    out = np.einsum("nkhw,ck->nchw", np.asarray(corr, dtype=np.float64), w)
+    if bias is not None:
+        out = out + np.asarray(bias, dtype=np.float64).reshape(1, -1, 1, 1)
+    if relu:
+        out = np.maximum(out, 0.0)
+    return out.astype(np.float32)

@@ -52,11 +52,17 @@ def upsample_flow(flow, mask):
     return _UpsampleFn.apply(flow, mask)
 
 
-def patch_raft(raft_module):
+def patch_raft(raft_module, fuse_motion_encoder=False):
     """Installs CorrBlock / AlternateCorrBlock at the module globals core/raft.py:187,189 looks up and the fused
-    convex upsampling as RAFT.upsample_flow (core/raft.py:112,240).  Returns the replaced objects."""
+    convex upsampling as RAFT.upsample_flow (core/raft.py:112,240).  Returns the replaced objects.
+    fuse_motion_encoder=True additionally defers every lookup into the motion encoder's first layer (fused.py:
+    one kernel for corr_fn(coords1) + relu(convc1(.)), inference only); undo that part with the function stored as
+    ``raft_module._rcb_undo_fused``."""
     from .corr import AlternateCorrBlock, CorrBlock
     old = (raft_module.CorrBlock, raft_module.AlternateCorrBlock, raft_module.RAFT.upsample_flow)
     raft_module.CorrBlock, raft_module.AlternateCorrBlock = CorrBlock, AlternateCorrBlock
     raft_module.RAFT.upsample_flow = lambda self, flow, mask: upsample_flow(flow, mask)
+    if fuse_motion_encoder:
+        from .fused import install_fused_motion_encoder
+        raft_module._rcb_undo_fused = install_fused_motion_encoder(raft_module)
     return old

@@ -219,12 +219,30 @@ def case_upsample_flow():
          out=out.detach().numpy(), dflow=flow.grad.numpy(), dmask=mask.grad.numpy())
 
 
+def case_motion_encoder_convc1():
+    """Lookup followed by the motion encoder's first layer, cor = relu(convc1(corr)) (core/update.py:154,202), with the
+    reference's own encoder modules (seeded default initialisation) on the reference CorrBlock output."""
+    import argparse as ap
+    import update as update_mod
+    for name, enc_cls, r, seed, dims in (("basic", update_mod.BasicMotionEncoder, 4, 81, (2, 32, 16, 24)),
+                                         ("small", update_mod.SmallMotionEncoder, 3, 82, (1, 24, 17, 19))):
+        B, C, H, W = dims
+        f1, f2, coords = make_inputs(seed, B, C, H, W, sigma=2.5)
+        torch.manual_seed(seed)
+        enc = enc_cls(ap.Namespace(corr_levels=4, corr_radius=r))
+        with torch.no_grad():
+            corr = CorrBlock(torch.from_numpy(f1), torch.from_numpy(f2), num_levels=4, radius=r)(torch.from_numpy(coords))
+            cor = torch.relu(enc.convc1(corr))
+        save("convc1_" + name, meta=np.array([B, C, H, W, 4, r, seed]), fmap1=f1, fmap2=f2, coords=coords,
+             weight=enc.convc1.weight.detach().numpy(), bias=enc.convc1.bias.detach().numpy(), cor=cor.numpy())
+
+
 if __name__ == "__main__":
     p = argparse.ArgumentParser()
     p.add_argument("--only", default=None)
     a = p.parse_args()
     cases = [case_odd, case_full, case_small, case_edges, case_known_answers, case_alt_formulation,
-             case_raft_small_crop, case_upsample_flow]
+             case_raft_small_crop, case_upsample_flow, case_motion_encoder_convc1]
     for c in cases:
         if a.only is None or a.only in c.__name__:
             c()

@@ -114,6 +114,40 @@ def test_patch_raft_with_fused_upsampling_matches_reference(ref):
         raft_mod.CorrBlock, raft_mod.AlternateCorrBlock, raft_mod.RAFT.upsample_flow = old
 
 
+@pytest.mark.parametrize("iters", [12, 32])
+def test_fused_motion_encoder_flow_matches_reference(ref, iters):
+    """patch_raft(fuse_motion_encoder=True): every corr_fn(coords1) + relu(convc1(corr)) pair of the unmodified
+    reference model (core/raft.py:219, core/update.py:154) becomes one fused launch; same EPE bound as the other modes."""
+    import raft_optical_flow_b200 as rcb
+    from raft_optical_flow_b200 import fused
+    d, raft_mod, ref_corr, InputPadder = ref
+    model, i1, i2 = _load(d, raft_mod, InputPadder, alternate=False)
+    want = _flow(model, i1, i2, iters)
+    calls = {"fused": 0}
+    real = rcb.CorrBlock.lookup_conv
+
+    def counting(self, *a, **k):
+        calls["fused"] += 1
+        return real(self, *a, **k)
+
+    old = rcb.patch_raft(raft_mod, fuse_motion_encoder=True)
+    rcb.CorrBlock.lookup_conv = counting
+    try:
+        assert raft_mod.CorrBlock is fused.LazyCorrBlock
+        mean, mx = _epe(_flow(model, i1, i2, iters), want)
+        print(f"fused motion encoder, iters={iters}: EPE delta mean {mean:.2e} px, max {mx:.2e} px")
+        assert calls["fused"] == iters
+        assert mean <= 0.01 and mx <= 0.05
+        preds = model(i1[:, :, :128, :256].contiguous(), i2[:, :, :128, :256].contiguous(), iters=2)  # autograd on
+        assert calls["fused"] == iters and preds[-1].requires_grad  # the unfused pair ran, and it is differentiable
+    finally:
+        rcb.CorrBlock.lookup_conv = real
+        raft_mod._rcb_undo_fused()
+        raft_mod.CorrBlock, raft_mod.AlternateCorrBlock, raft_mod.RAFT.upsample_flow = old
+    upd = sys.modules[raft_mod.BasicUpdateBlock.__module__]
+    assert not hasattr(upd.SmallMotionEncoder.forward, "_rcb_original")
+
+
 def test_alternate_corr_dropin_flow_matches_reference(ref):
     """--alternate_corr: (a) our AlternateCorrBlock patched in; (b) the reference's own AlternateCorrBlock running
     on top of our `alt_cuda_corr` module (extension-level drop-in, core/corr.py:6,190)."""

@@ -234,3 +234,35 @@ def test_upsample_kernels_stay_inside_their_buffers(cabi, dev, dims):
     dflow.check("upsample backward dflow")
     dmask.check("upsample backward dmask")
     ws.check("upsample backward workspace")
+
+
+@pytest.mark.parametrize("shape,radius,cout", [((2, 32, 13, 22), 4, 256), ((1, 24, 17, 19), 3, 96),
+                                               ((1, 16, 9, 130), 4, 16)])
+def test_fused_lookup_convc1_stays_inside_its_buffers(cabi, dev, shape, radius, cout):
+    B, C, H, W = shape
+    lib = cabi.lib()
+    f1, f2, coords = _inputs(B, C, H, W, dev)
+    levels = 4 if min(H, W) >= 16 else 3
+    lay = cabi.pyramid_layout(B, H, W, levels, cabi.F32)
+    lv = [torch.empty(lay.level_bytes[l] // 4, device=dev) for l in range(levels)]
+    ptrs = cabi.ptr_array([x.data_ptr() for x in lv])
+    m = cabi.BUILD_MODES["bf16x3"]
+    nws = lib.rcb_corr_build_workspace_bytes(B, C, H, W, m)
+    ws = torch.empty(max(nws, 16), dtype=torch.uint8, device=dev)
+    cabi.check(lib.rcb_corr_build(f1.data_ptr(), f2.data_ptr(), ptrs, B, C, H, W, levels, m, cabi.F32, ws.data_ptr(),
+                                  nws, _stream()), "rcb_corr_build")
+    plan = cabi.LookupPlan(ptrs, B, H, W, levels, radius, cabi.F32)
+    cin = levels * (2 * radius + 1) ** 2
+    weight = torch.randn(cout, cin, device=dev) / cin ** 0.5
+    bias = torch.randn(cout, device=dev)
+    npk = lib.rcb_corr_convc1_pack_bytes(cout, levels, radius)
+    assert npk > 0
+    wp = Guarded(npk, dev)
+    cabi.check(lib.rcb_corr_convc1_pack(weight.data_ptr(), wp.ptr, cout, levels, radius, _stream()),
+               "rcb_corr_convc1_pack")
+    wp.check("convc1 weight pack")
+    out = Guarded(B * cout * H * W * 4, dev)
+    cabi.check(lib.rcb_corr_lookup_convc1(plan.ptr, coords.data_ptr(), wp.ptr, bias.data_ptr(), out.ptr, cout, 1,
+                                          _stream()), "rcb_corr_lookup_convc1")
+    out.check("fused lookup + convc1")
+    assert torch.isfinite(out.view(torch.float32, (B, cout, H, W))).all()

@@ -457,3 +457,85 @@ def test_upsample_flow_vs_oracle(rcb, dev, orc, dims):
     flat = rcb.upsample_flow(t(flow, dev), torch.zeros(N, 576, H, W, device=dev)).cpu().numpy()
     assert rel_err(flat, orc.upsample_flow(flow, np.zeros_like(mask))) < TOL
     assert np.abs(flat[:, :, ::8, ::8] - flat[:, :, 7::8, 7::8]).max() < 1e-5  # constant inside a coarse cell
+
+
+# ---------------------------------------------------------------------------------------------
+# (9) lookup fused with the motion encoder's first layer (scope table 8f, f1): relu(convc1(corr))
+# fp16 tensor-core operands, fp32 accumulate -> the stated bound is 1e-3 of max-abs of the fp32 result (measured
+# 3e-4); the reference itself runs this convolution in TF32 (same 11-bit significands) under cuDNN's defaults.
+# ---------------------------------------------------------------------------------------------
+CONVC1_TOL = 1e-3
+
+
+@pytest.mark.parametrize("name", ["convc1_basic", "convc1_small"])
+def test_lookup_convc1_golden(rcb, dev, name):
+    g = load_golden(name)
+    B, C, H, W, L, r, _ = [int(v) for v in g["meta"]]
+    blk = rcb.CorrBlock(t(g["fmap1"], dev), t(g["fmap2"], dev), num_levels=L, radius=r)
+    packed = rcb.PackedConvC1(t(g["weight"], dev), t(g["bias"], dev), L, r)
+    got = blk.lookup_conv(t(g["coords"], dev), packed)
+    assert got.shape == g["cor"].shape and got.dtype == torch.float32 and got.is_contiguous()
+    assert rel_err(got.cpu().numpy(), g["cor"]) < CONVC1_TOL
+
+
+@pytest.mark.parametrize("relu,with_bias", [(True, True), (False, False)])
+@pytest.mark.parametrize("shape", [(2, 32, 23, 39, 4, 256), (1, 48, 30, 44, 3, 96), (3, 16, 16, 17, 4, 16),
+                                   (1, 32, 9, 130, 3, 80)])
+def test_lookup_convc1_vs_oracle(rcb, dev, orc, shape, relu, with_bias):
+    B, C, H, W, r, cout = shape  # Q = H*W is not a multiple of the 128-query tile
+    L = 4 if min(H, W) >= 16 else 3
+    f1, f2, coords = seeded(900 + cout, B, C, H, W, sigma=3.0)
+    coords[:, :, 0, 0] = -40.0  # a window entirely outside
+    rs = np.random.RandomState(cout)
+    cin = L * (2 * r + 1) ** 2
+    weight = (rs.standard_normal((cout, cin, 1, 1)) / np.sqrt(cin)).astype(np.float32)
+    bias = (0.2 * rs.standard_normal(cout)).astype(np.float32) if with_bias else None
+    blk = rcb.CorrBlock(t(f1, dev), t(f2, dev), num_levels=L, radius=r)
+    packed = rcb.PackedConvC1(t(weight, dev), None if bias is None else t(bias, dev), L, r)
+    got = blk.lookup_conv(t(coords, dev), packed, relu=relu).cpu().numpy()
+    want = orc.convc1_relu(orc.OracleCorrBlock(f1, f2, num_levels=L, radius=r)(coords, roundtrip=False), weight, bias,
+                           relu=relu)
+    assert np.isfinite(got).all()
+    assert rel_err(got, want) < CONVC1_TOL
+
+
+def test_lookup_convc1_full_size_matches_unfused_pair(rcb, dev):
+    """cfg2 geometry: the fused kernel against its own unfused pair (lookup, then an fp32 torch convolution)."""
+    B, C, H, W, r, L, cout = 2, 256, 55, 128, 4, 4, 256
+    f1, f2, coords = seeded(31, B, C, H, W)
+    rs = np.random.RandomState(5)
+    cin = L * (2 * r + 1) ** 2
+    weight = t((rs.standard_normal((cout, cin, 1, 1)) / np.sqrt(cin)).astype(np.float32), dev)
+    bias = t((0.1 * rs.standard_normal(cout)).astype(np.float32), dev)
+    blk = rcb.CorrBlock(t(f1, dev), t(f2, dev), num_levels=L, radius=r)
+    packed = rcb.PackedConvC1(weight, bias, L, r)
+    c = t(coords, dev)
+    got = blk.lookup_conv(c, packed)
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        want = torch.relu(torch.nn.functional.conv2d(blk(c), weight, bias))
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    assert rel_err(got.cpu().numpy(), want.cpu().numpy()) < CONVC1_TOL
+    # output channels are independent: permuting the rows of the weight permutes the result bit for bit
+    perm = torch.from_numpy(np.random.RandomState(6).permutation(cout)).to(dev)
+    p2 = rcb.PackedConvC1(weight[perm].contiguous(), bias[perm].contiguous(), L, r)
+    assert torch.equal(blk.lookup_conv(c, p2), got[:, perm])
+
+
+def test_lookup_convc1_rejects_what_it_does_not_support(rcb, dev):
+    f1, f2, coords = seeded(3, 1, 16, 16, 24)
+    w = torch.randn(32, 4 * 81, 1, 1, device=dev)
+    blk16 = rcb.CorrBlock(t(f1, dev), t(f2, dev), pyramid_dtype="f16")
+    with pytest.raises(RuntimeError):
+        blk16.lookup_conv(t(coords, dev), rcb.PackedConvC1(w, None))
+    with pytest.raises(RuntimeError):
+        rcb.PackedConvC1(torch.randn(32, 100, 1, 1, device=dev), None)  # wrong input channel count
+    with pytest.raises(RuntimeError):
+        rcb.PackedConvC1(torch.randn(24, 4 * 81, 1, 1, device=dev), None)  # cout not a multiple of 16
+    with pytest.raises(RuntimeError):
+        rcb.PackedConvC1(w.cpu(), None)
+    blk = rcb.CorrBlock(t(f1, dev), t(f2, dev), radius=3)
+    with pytest.raises(RuntimeError):
+        blk.lookup_conv(t(coords, dev), rcb.PackedConvC1(w, None))  # packed for radius 4

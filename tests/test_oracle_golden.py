@@ -177,3 +177,12 @@ def test_upsample_flow_oracle_matches_reference_golden():
     dflow, dmask = orc.upsample_flow_backward(g["flow"], g["mask"], cotangent(seed, g["out"].shape))
     assert rel_err(dflow, g["dflow"]) < 1e-4
     assert rel_err(dmask, g["dmask"]) < 1e-4
+
+
+@pytest.mark.parametrize("name", ["convc1_basic", "convc1_small"])
+def test_lookup_convc1_oracle_matches_reference_golden(name):
+    """oracle lookup + convc1_relu vs the reference CorrBlock followed by the reference motion encoder's convc1 and
+    ReLU (core/update.py:154,202)."""
+    g = load_golden(name)
+    blk, L, r = _block(g)
+    assert rel_err(orc.convc1_relu(blk(g["coords"]), g["weight"], g["bias"]), g["cor"]) < 1e-5
