@@ -41,8 +41,9 @@ struct Cfg {
   static constexpr int RP = RD + 1;                        // window row padded to an even number of halfs
   static constexpr int KL = (RD * RP + 15) / 16 * 16;      // K entries per level: 96 (r = 4), 64 (r = 3)
   static constexpr int BM = 128;
-  static constexpr int MATH_WARPS = 16;                    // 8 queries each
-  static constexpr int THREADS = 32 * (MATH_WARPS + 2);
+  static constexpr int MATH_WARPS = 8;                     // two groups of 8 queries each
+  static constexpr int EPI_WARPS = 4;                       // one per tensor-memory lane quarter
+  static constexpr int THREADS = 32 * (MATH_WARPS + EPI_WARPS + 2);
   static constexpr int SLOT_BYTES = G::SLOT_BYTES;
   static constexpr int WARP_RING = 8 * SLOT_BYTES;
   static constexpr int MAX_N = 256;
@@ -51,10 +52,11 @@ struct Cfg {
   static constexpr int B_BYTES = (KL / 8) * MAX_N * 16;    // one level of weights: [K/8][N][16 B]
   static constexpr int OFF_B = 2 * A_BUF_BYTES;
   static constexpr int OFF_RING = OFF_B + B_BYTES;
-  static constexpr int OFF_BIAS = OFF_RING + MATH_WARPS * WARP_RING;
+  static constexpr int OFF_BIAS = OFF_RING + 2 * MATH_WARPS * WARP_RING;
   static constexpr int OFF_BAR = OFF_BIAS + MAX_N * 4;
-  // barriers: gather[16], level_done[4], a_free[2], b_full, b_empty, acc_full, then the tensor-memory slot
-  static constexpr int NBAR = MATH_WARPS + RCB_MAX_LEVELS + 2 + 3;
+  // barriers: gather[2 per warp], level_done[4], a_free[2], acc_full[2], d_free[2], b_full[2], b_empty[2], then the
+  // tensor-memory slot
+  static constexpr int NBAR = 2 * MATH_WARPS + RCB_MAX_LEVELS + 10;
   static constexpr int SMEM_BYTES = OFF_BAR + 8 * NBAR + 16;
   static constexpr int SMEM_ALLOC = SMEM_BYTES + 128;      // the base is rounded up to 128 bytes (TMA destinations)
 };
@@ -76,7 +78,7 @@ template <int R>
 __global__ void __launch_bounds__(Cfg<R>::THREADS, 1)
 lookup_conv_kernel(const __grid_constant__ LookupMaps maps, PyramidDev pyr, const float* __restrict__ coords,
                    const __half* __restrict__ wpack, const float* __restrict__ bias, float* __restrict__ out, int Q,
-                   int L, int N, int relu) {
+                   int L, int N, int relu, int tiles_q, int ntiles, int dbg) {
   using C = Cfg<R>;
   using G = typename C::G;
   constexpr int RD = C::RD, RP = C::RP, KL = C::KL, ROWS = G::ROWS, NMIN = G::NMIN, NMAX = G::NMAX;
@@ -87,194 +89,265 @@ lookup_conv_kernel(const __grid_constant__ LookupMaps maps, PyramidDev pyr, cons
   unsigned char* smem = smem_raw + (base - raw);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int b = blockIdx.y;
-  const int q0 = blockIdx.x * C::BM;
   const uint32_t bar0 = base + C::OFF_BAR;
   auto gbar = [&](int w) { return bar0 + 8 * w; };
-  auto level_done = [&](int l) { return bar0 + 8 * (MW + l); };
-  auto a_free = [&](int i) { return bar0 + 8 * (MW + RCB_MAX_LEVELS + i); };
-  const uint32_t b_full = bar0 + 8 * (MW + RCB_MAX_LEVELS + 2);
-  const uint32_t b_empty = b_full + 8;
-  const uint32_t acc_full = b_full + 16;
-  const uint32_t tmem_slot = b_full + 24;
+  auto level_done = [&](int l) { return bar0 + 8 * (2 * MW + l); };
+  auto a_free = [&](int i) { return bar0 + 8 * (2 * MW + RCB_MAX_LEVELS + i); };
+  auto acc_full = [&](int d) { return bar0 + 8 * (2 * MW + RCB_MAX_LEVELS + 2 + d); };
+  auto d_free = [&](int d) { return bar0 + 8 * (2 * MW + RCB_MAX_LEVELS + 4 + d); };
+  auto b_full = [&](int i) { return bar0 + 8 * (2 * MW + RCB_MAX_LEVELS + 6 + i); };
+  auto b_empty = [&](int i) { return bar0 + 8 * (2 * MW + RCB_MAX_LEVELS + 8 + i); };
+  constexpr int EW0 = MW, PW = MW + C::EPI_WARPS, TW = MW + C::EPI_WARPS + 1;  // first epilogue / producer / MMA warp
+  const uint32_t tmem_slot = bar0 + 8 * C::NBAR;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + C::OFF_BAR + 8 * C::NBAR);
   float* sbias = reinterpret_cast<float*>(smem + C::OFF_BIAS);
 
   if (tid == 0) {
-    for (int w = 0; w < MW; ++w) mbar_init(gbar(w), 8);
+    for (int w = 0; w < 2 * MW; ++w) mbar_init(gbar(w), 8);
     for (int l = 0; l < RCB_MAX_LEVELS; ++l) mbar_init(level_done(l), MW);
-    mbar_init(a_free(0), 1);
-    mbar_init(a_free(1), 1);
-    mbar_init(b_full, 1);
-    mbar_init(b_empty, 1);
-    mbar_init(acc_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(a_free(i), 1);
+      mbar_init(acc_full(i), 1);
+      mbar_init(d_free(i), C::EPI_WARPS);
+      mbar_init(b_full(i), 1);
+      mbar_init(b_empty(i), 1);
+    }
     fence_barrier_init();
   }
   if (tid < N) sbias[tid] = bias ? __ldg(bias + tid) : 0.f;
-  if (warp == MW + 1) tc::tmem_alloc<1>(tmem_slot, 256);
+  if (warp == TW) tc::tmem_alloc<1>(tmem_slot, 512);  // two accumulators: tile i and tile i + 1
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  const int tile0 = blockIdx.x, tstep = gridDim.x;
 
-  if (warp == MW) {
-    // ---- weight producer: the level's [KL/8][N][8] fp16 block in one bulk copy ----
-    const uint32_t bytes = (uint32_t)(KL * N * 2);
-    for (int l = 0; l < L; ++l) {
-      mbar_wait(b_empty, (uint32_t)((l & 1) ^ 1));
-      if (elect_one()) {
-        mbar_expect_tx(b_full, bytes);
-        bulk_load(base + C::OFF_B, wpack + (long long)l * KL * N, bytes, b_full);
-      }
-      __syncwarp();
-    }
-  } else if (warp == MW + 1) {
-    // ---- MMA issuer: KL/16 K steps per level as soon as the level's samples and weights are in place ----
-    const uint32_t idesc = tc::make_idesc_f16_mn(C::BM, N);
-    uint32_t acc = 0;
-    for (int l = 0; l < L; ++l) {
-      mbar_wait(level_done(l), 0);
-      mbar_wait(b_full, (uint32_t)(l & 1));
-      tc_fence_after();
-      if (elect_one()) {
-        const uint32_t a_addr = base + (l & 1) * C::A_BUF_BYTES;
-        const uint32_t b_addr = base + C::OFF_B;
-#pragma unroll
-        for (int t = 0; t < KL / 16; ++t) {
-          const uint64_t adesc = make_desc_interleaved(a_addr + t * 2 * C::A_LBO, C::A_LBO, 128);
-          const uint64_t bdesc = make_desc_interleaved(b_addr + t * 2 * N * 16, (uint32_t)N * 16, 128);
-          tc::umma_bf16_ss(tmem_base, adesc, bdesc, idesc, acc);
-          acc = 1;
+  if (warp == PW) {
+    // ---- weight producer: half a level's [KL/16][N][8] fp16 block per bulk copy, two buffers, so the weights of a
+    // level are resident before its samples are and the MMAs start the moment the level completes ----
+    const uint32_t bytes = (uint32_t)(KL / 2 * N * 2);
+    int c = 0;
+    for (int tile = tile0; tile < ntiles; tile += tstep) {
+      for (int l2 = 0; l2 < 2 * L; ++l2, ++c) {
+        mbar_wait(b_empty(c & 1), (uint32_t)(((c >> 1) & 1) ^ 1));
+        if (elect_one()) {
+          mbar_expect_tx(b_full(c & 1), bytes);
+          bulk_load(base + C::OFF_B + (c & 1) * (C::B_BYTES / 2), wpack + (long long)l2 * (KL / 2) * N, bytes,
+                    b_full(c & 1));
         }
-        tc::umma_commit<1>(b_empty);
-        tc::umma_commit<1>(a_free(l & 1));
+        __syncwarp();
       }
-      acc = 1;
-      __syncwarp();
     }
-    if (elect_one()) tc::umma_commit<1>(acc_full);
-    __syncwarp();
+  } else if (warp == TW) {
+    // ---- MMA issuer: KL/16 K steps per level as soon as the level's samples are in place ----
+    const uint32_t idesc = tc::make_idesc_f16_mn(C::BM, N);
+    int g = 0, i = 0, c = 0;
+    for (int tile = tile0; tile < ntiles; tile += tstep, ++i) {
+      const int d = i & 1;
+      if (i >= 2) mbar_wait(d_free(d), (uint32_t)(((i >> 1) - 1) & 1));  // the epilogue of tile i - 2 has read it
+      for (int l = 0; l < L; ++l, ++g) {
+        mbar_wait(level_done(l), (uint32_t)(i & 1));
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf, ++c) {
+          mbar_wait(b_full(c & 1), (uint32_t)((c >> 1) & 1));
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t a_addr = base + (g & 1) * C::A_BUF_BYTES + hf * (KL / 16) * C::A_LBO;
+            const uint32_t b_addr = base + C::OFF_B + (c & 1) * (C::B_BYTES / 2);
+#pragma unroll
+            for (int t = 0; t < KL / 32; ++t) {
+              if (dbg & 1) break;  // timing experiment: no MMAs
+              const uint64_t adesc = make_desc_interleaved(a_addr + t * 2 * C::A_LBO, C::A_LBO, 128);
+              const uint64_t bdesc = make_desc_interleaved(b_addr + t * 2 * N * 16, (uint32_t)N * 16, 128);
+              tc::umma_bf16_ss(tmem_base + 256 * d, adesc, bdesc, idesc, (l > 0 || hf > 0 || t > 0) ? 1u : 0u);
+            }
+            tc::umma_commit<1>(b_empty(c & 1));
+            if (hf == 1) {
+              tc::umma_commit<1>(a_free(g & 1));
+              if (l == L - 1) tc::umma_commit<1>(acc_full(d));
+            }
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp >= EW0) {
+    // ---- epilogue: lane = query, registers = output channels; bias, ReLU, 128-byte coalesced stores ----
+    const int quarter = warp & 3;
+    int i = 0;
+    for (int tile = tile0; tile < ntiles; tile += tstep, ++i) {
+      const int d = i & 1;
+      const int bb = tile / tiles_q, qe = (tile % tiles_q) * C::BM + quarter * 32 + lane;
+      mbar_wait(acc_full(d), (uint32_t)((i >> 1) & 1));
+      tc_fence_after();
+      float* o = out + (long long)bb * N * Q + qe;
+      for (int n0 = 0; n0 < N; n0 += 32) {
+        float v[32];
+        tc::tmem_ld32(tmem_base + 256 * d + ((uint32_t)(quarter * 32) << 16) + n0, v);
+        if (n0 + 32 >= N) {  // the accumulator may be overwritten by the MMAs of tile i + 2
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(d_free(d));
+        }
+        if (qe < Q && !(dbg & 8)) {
+#pragma unroll
+          for (int k = 0; k < 32; ++k) {
+            if (n0 + k < N) {
+              float x = v[k] + sbias[n0 + k];
+              if (relu) x = fmaxf(x, 0.f);
+              o[(long long)(n0 + k) * Q] = x;
+            }
+          }
+        }
+      }
+    }
   } else {
     // ---- gather + resample into the level's A operand ----
+    // A warp owns two groups of 8 queries (h = 0, 1), each with its own slots and mbarrier: while it resamples one
+    // group, the gather of the other is in flight, and every finished chunk immediately issues the gather of the
+    // same group's next level (or of the next tile's first level).
     const int ql = lane >> 2, sub = lane & 3;
-    const uint32_t bar = gbar(warp);
-    const float4* slot = reinterpret_cast<const float4*>(smem + C::OFF_RING + warp * C::WARP_RING + ql * C::SLOT_BYTES);
-    const uint32_t slot_addr = base + C::OFF_RING + warp * C::WARP_RING + ql * C::SLOT_BYTES;
-    const int m = warp * 8 + ql;  // row of the A tile
-    const int q = q0 + m;
-    const bool q_ok = q < Q;
-    float cx = -1.0e6f, cy = -1.0e6f;
-    if (q_ok) {
-      cx = __ldg(coords + (long long)(b * 2 + 0) * Q + q);
-      cy = __ldg(coords + (long long)(b * 2 + 1) * Q + q);
-    }
     const int b0 = (RD * sub) >> 2, nb = ((RD * (sub + 1)) >> 2) - b0;  // output rows [b0, b0 + nb), nb <= NBMAX
-    for (int l = 0; l < L; ++l) {
-      const int Hl = l == 0 ? pyr.H[0] : l == 1 ? pyr.H[1] : l == 2 ? pyr.H[2] : pyr.H[3];
-      const int Wl = l == 0 ? pyr.W[0] : l == 1 ? pyr.W[1] : l == 2 ? pyr.W[2] : pyr.W[3];
-      const LevelCoord lc = level_coord<R>(cx, cy, l, Hl, Wl);
-      const int ph = lc.xs & 3, py = lc.ys & 3;
-      const int nx = (ph + ROWS + 3) >> 2, ny = (py + ROWS + 3) >> 2;
+
+    struct Pending {
+      LevelCoord lc;
+      int Hl, Wl;
+      bool ok;
+    };
+    auto load_coords = [&](int tile, int h, float& cx, float& cy) {
+      const int bb = tile / tiles_q, q = (tile % tiles_q) * C::BM + (warp + MW * h) * 8 + ql;
+      cx = cy = -1.0e6f;
+      if (tile < ntiles && q < Q) {
+        cx = __ldg(coords + (long long)(bb * 2 + 0) * Q + q);
+        cy = __ldg(coords + (long long)(bb * 2 + 1) * Q + q);
+      }
+    };
+    auto issue = [&](int tile, int l, int h, float cx, float cy) {
+      Pending p;
+      const int bb = tile / tiles_q, q = (tile % tiles_q) * C::BM + (warp + MW * h) * 8 + ql;
+      p.ok = q < Q;
+      p.Hl = l == 0 ? pyr.H[0] : l == 1 ? pyr.H[1] : l == 2 ? pyr.H[2] : pyr.H[3];
+      p.Wl = l == 0 ? pyr.W[0] : l == 1 ? pyr.W[1] : l == 2 ? pyr.W[2] : pyr.W[3];
+      p.lc = level_coord<R>(cx, cy, l, p.Hl, p.Wl);
       if (sub == 0) {
-        if (q_ok) {
+        const uint32_t bar = gbar(2 * warp + h);
+        if (p.ok && !(dbg & 2)) {
+          const int nx = ((p.lc.xs & 3) + ROWS + 3) >> 2, ny = ((p.lc.ys & 3) + ROWS + 3) >> 2;
           mbar_expect_tx(bar, (uint32_t)(nx * ny * 64));
-          tma_load_3d(slot_addr, &maps.m[l * 4 + (ny - NMIN) * 2 + (nx - NMIN)], bar, (lc.xs >> 2) * 16, lc.ys >> 2,
-                      b * Q + q);
+          tma_load_3d(base + C::OFF_RING + (2 * warp + h) * C::WARP_RING + ql * C::SLOT_BYTES,
+                      &maps.m[l * 4 + (ny - NMIN) * 2 + (nx - NMIN)], bar, (p.lc.xs >> 2) * 16, p.lc.ys >> 2,
+                      bb * Q + q);
         } else {
           mbar_arrive(bar);
         }
       }
-      if (l >= 2) mbar_wait(a_free(l & 1), 0);  // the MMAs of level l - 2 have read this buffer
-      mbar_wait(bar, (uint32_t)(l & 1));
-      if (q_ok) {
-        const float fx = lc.fx, fy = lc.fy, gx = 1.0f - lc.fx, gy = 1.0f - lc.fy;
-        const bool ragged_w = (Wl & 3) != 0;
-        unsigned char* arow = smem + (l & 1) * C::A_BUF_BYTES + m * 16;
-        auto a_store = [&](int kbyte, uint32_t v) {  // kbyte: byte offset inside the level's K row, multiple of 4
-          *reinterpret_cast<uint32_t*>(arow + (kbyte >> 4) * C::A_LBO + (kbyte & 15)) = v;
-        };
-        float hp[RD];
+      return p;
+    };
+    // resamples the gathered windows of group h and writes them into rows of A buffer `abuf`
+    auto consume = [&](const Pending& cur, int h, int abuf) {
+      if (!cur.ok || (dbg & 4)) return;
+      const float4* slot =
+          reinterpret_cast<const float4*>(smem + C::OFF_RING + (2 * warp + h) * C::WARP_RING + ql * C::SLOT_BYTES);
+      const int m = (warp + MW * h) * 8 + ql;  // row of the A tile
+      const LevelCoord lc = cur.lc;
+      const int Hl = cur.Hl, Wl = cur.Wl;
+      const int ph = lc.xs & 3, py = lc.ys & 3;
+      const int nx = (ph + ROWS + 3) >> 2;
+      const float fx = lc.fx, fy = lc.fy, gx = 1.0f - lc.fx, gy = 1.0f - lc.fy;
+      const bool ragged_w = (Wl & 3) != 0;
+      unsigned char* arow = smem + abuf * C::A_BUF_BYTES + m * 16;
+      auto a_store = [&](int kbyte, uint32_t v) {  // kbyte: byte offset inside the level's K row, multiple of 4
+        *reinterpret_cast<uint32_t*>(arow + (kbyte >> 4) * C::A_LBO + (kbyte & 15)) = v;
+      };
+      float hp[RD];
 #pragma unroll
-        for (int jj = 0; jj <= NBMAX; ++jj) {
-          if (jj > nb) break;
-          const int j = b0 + jj;  // window row
-          const int ya = py + j;  // row inside the fetched box
-          const bool row_ok = lc.ys + j < Hl;
-          const float4* rowp = slot + ((ya >> 2) * nx) * 4 + (ya & 3);
-          float w[4 * NMAX];
+      for (int jj = 0; jj <= NBMAX; ++jj) {
+        if (jj > nb) break;
+        const int j = b0 + jj;  // window row
+        const int ya = py + j;  // row inside the fetched box
+        const bool row_ok = lc.ys + j < Hl;
+        const float4* rowp = slot + ((ya >> 2) * nx) * 4 + (ya & 3);
+        float w[4 * NMAX];
 #pragma unroll
-          for (int k = 0; k < NMAX; ++k) {
-            float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (row_ok && k < nx) u = rowp[k * 4];
-            w[4 * k + 0] = u.x; w[4 * k + 1] = u.y; w[4 * k + 2] = u.z; w[4 * k + 3] = u.w;
-          }
-          float v1[ROWS + 2];
-#pragma unroll
-          for (int i = 0; i < ROWS + 2; ++i) v1[i] = (ph & 1) ? w[i + 1] : w[i];
-          float t[ROWS];
-#pragma unroll
-          for (int i = 0; i < ROWS; ++i) t[i] = (ph & 2) ? v1[i + 2] : v1[i];
-          if (ragged_w) {
-#pragma unroll
-            for (int i = 0; i < ROWS; ++i)
-              if (lc.xs + i >= Wl) t[i] = 0.f;
-          }
-          float hh[RD];
-#pragma unroll
-          for (int a = 0; a < RD; ++a) hh[a] = gx * t[a] + fx * t[a + 1];
-          if (jj > 0) {
-            const int kb = (j - 1) * RP * 2;
-#pragma unroll
-            for (int a2 = 0; a2 < RP / 2; ++a2) {
-              const float o0 = gy * hp[2 * a2] + fy * hh[2 * a2];
-              const float o1 = (2 * a2 + 1 < RD) ? gy * hp[(2 * a2 + 1) % RD] + fy * hh[(2 * a2 + 1) % RD] : 0.f;
-              const __half2 hv = __floats2half2_rn(o0, o1);
-              a_store(kb + 4 * a2, *reinterpret_cast<const uint32_t*>(&hv));
-            }
-          }
-#pragma unroll
-          for (int a = 0; a < RD; ++a) hp[a] = hh[a];
+        for (int k = 0; k < NMAX; ++k) {
+          float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (row_ok && k < nx) u = rowp[k * 4];
+          w[4 * k + 0] = u.x; w[4 * k + 1] = u.y; w[4 * k + 2] = u.z; w[4 * k + 3] = u.w;
         }
-        if (sub == 3) {  // the level's trailing K padding must be finite: zeros
+        float v1[ROWS + 2];
 #pragma unroll
-          for (int i = 0; i < (KL - RD * RP) / 2; ++i) a_store(RD * RP * 2 + 4 * i, 0u);
+        for (int k = 0; k < ROWS + 2; ++k) v1[k] = (ph & 1) ? w[k + 1] : w[k];
+        float t[ROWS];
+#pragma unroll
+        for (int k = 0; k < ROWS; ++k) t[k] = (ph & 2) ? v1[k + 2] : v1[k];
+        if (ragged_w) {
+#pragma unroll
+          for (int k = 0; k < ROWS; ++k)
+            if (lc.xs + k >= Wl) t[k] = 0.f;
+        }
+        float hh[RD];
+#pragma unroll
+        for (int a = 0; a < RD; ++a) hh[a] = gx * t[a] + fx * t[a + 1];
+        if (jj > 0) {
+          const int kb = (j - 1) * RP * 2;
+#pragma unroll
+          for (int a2 = 0; a2 < RP / 2; ++a2) {
+            const float o0 = gy * hp[2 * a2] + fy * hh[2 * a2];
+            const float o1 = (2 * a2 + 1 < RD) ? gy * hp[(2 * a2 + 1) % RD] + fy * hh[(2 * a2 + 1) % RD] : 0.f;
+            const __half2 hv = __floats2half2_rn(o0, o1);
+            a_store(kb + 4 * a2, *reinterpret_cast<const uint32_t*>(&hv));
+          }
+        }
+#pragma unroll
+        for (int a = 0; a < RD; ++a) hp[a] = hh[a];
+      }
+      if (sub == 3) {  // the level's trailing K padding must be finite: zeros
+#pragma unroll
+        for (int k = 0; k < (KL - RD * RP) / 2; ++k) a_store(RD * RP * 2 + 4 * k, 0u);
+      }
+    };
+    float cx0, cy0, cx1, cy1, cxn0, cyn0, cxn1, cyn1;
+    load_coords(tile0, 0, cx0, cy0);
+    load_coords(tile0, 1, cx1, cy1);
+    Pending pend0 = issue(tile0, 0, 0, cx0, cy0);
+    Pending pend1 = issue(tile0, 0, 1, cx1, cy1);
+    int cnt = 0, g = 0;
+    for (int tile = tile0; tile < ntiles; tile += tstep) {
+      const int next_tile = tile + tstep;
+      load_coords(next_tile, 0, cxn0, cyn0);
+      load_coords(next_tile, 1, cxn1, cyn1);
+      for (int l = 0; l < L; ++l, ++g, ++cnt) {
+        if (g >= 2) mbar_wait(a_free(g & 1), (uint32_t)(((g >> 1) - 1) & 1));  // the MMAs two levels back have read it
+        // group 0
+        mbar_wait(gbar(2 * warp), (uint32_t)(cnt & 1));
+        consume(pend0, 0, g & 1);
+        __syncwarp();  // every lane is done with the slots before the next gather lands in them
+        if (l + 1 < L) {
+          pend0 = issue(tile, l + 1, 0, cx0, cy0);
+        } else if (next_tile < ntiles) {
+          pend0 = issue(next_tile, 0, 0, cxn0, cyn0);
+        }
+        // group 1
+        mbar_wait(gbar(2 * warp + 1), (uint32_t)(cnt & 1));
+        consume(pend1, 1, g & 1);
+        fence_proxy_async_smem();  // A writes (both groups) -> visible to the tensor core's reads
+        __syncwarp();
+        if (lane == 0) mbar_arrive(level_done(l));
+        if (l + 1 < L) {
+          pend1 = issue(tile, l + 1, 1, cx1, cy1);
+        } else if (next_tile < ntiles) {
+          pend1 = issue(next_tile, 0, 1, cxn1, cyn1);
         }
       }
-      fence_proxy_async_smem();  // A writes -> visible to the tensor core's reads
-      __syncwarp();              // and every lane is done with the slots before the next gather lands in them
-      if (lane == 0) mbar_arrive(level_done(l));
-    }
-
-    // ---- epilogue: lane = query, registers = output channels ----
-    const int quarter = warp & 3, cblk = warp >> 2;
-    const int qe = q0 + quarter * 32 + lane;
-    mbar_wait(acc_full, 0);
-    tc_fence_after();
-    float* o = out + (long long)b * N * Q + qe;
-#pragma unroll
-    for (int cb = 0; cb < 2; ++cb) {
-      const int n0 = cblk * 64 + cb * 32;
-      if (n0 >= N) break;
-      float v[32];
-      tc::tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + n0, v);
-      if (qe < Q) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          if (n0 + i < N) {
-            float x = v[i] + sbias[n0 + i];
-            if (relu) x = fmaxf(x, 0.f);
-            o[(long long)(n0 + i) * Q] = x;
-          }
-        }
-      }
+      cx0 = cxn0; cy0 = cyn0; cx1 = cxn1; cy1 = cyn1;
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == MW + 1) {
+  if (warp == TW) {
     tc_fence_after();
-    tc::tmem_dealloc<1>(tmem_base, 256);
+    tc::tmem_dealloc<1>(tmem_base, 512);
   }
 }
 
@@ -312,9 +385,11 @@ static int launch_r(const LookupPlan& plan, const PyramidDev& pd, const float* c
   cudaError_t e = cudaFuncSetAttribute(lookup_conv_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        C::SMEM_ALLOC);
   if (e != cudaSuccess) return (int)e;
-  dim3 grid((Q + C::BM - 1) / C::BM, plan.B);
+  const int tiles_q = (Q + C::BM - 1) / C::BM, ntiles = tiles_q * plan.B;
+  static const int dbg = getenv("RCB_LCONV_DEBUG") ? atoi(getenv("RCB_LCONV_DEBUG")) : 0;  // timing experiments
+  const int grid = ntiles < kNumSMs ? ntiles : kNumSMs;  // persistent: one CTA per SM walks tiles grid apart
   lookup_conv_kernel<R><<<grid, C::THREADS, C::SMEM_ALLOC, s>>>(plan.maps, pd, coords, wpack, bias, out, Q,
-                                                                 plan.lay.levels, cout, relu);
+                                                                 plan.lay.levels, cout, relu, tiles_q, ntiles, dbg);
   return launch_status();
 }
 

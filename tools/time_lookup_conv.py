@@ -13,6 +13,7 @@ ap.add_argument("--cout", type=int, default=None)
 ap.add_argument("--reps", type=int, default=32)
 ap.add_argument("--batch", type=int, default=None)
 ap.add_argument("--check-only", action="store_true")
+ap.add_argument("--fused-only", action="store_true")
 a = ap.parse_args()
 B, C, H, W, r, L, iters, _ = CONFIGS[a.config]
 if a.batch:
@@ -59,6 +60,9 @@ def timeit(fn):
     return e0.elapsed_time(e1) / a.reps * 1e3
 
 t_fused = timeit(lambda c: blk.lookup_conv(c, packed))
+if a.fused_only:
+    print(f"debug={os.environ.get('RCB_LCONV_DEBUG', '0')} fused {t_fused:.1f} us")
+    sys.exit(0)
 t_lookup = timeit(lambda c: blk(c))
 t_pair32 = timeit(lambda c: F.relu(F.conv2d(blk(c), weight, bias)))
 torch.backends.cudnn.allow_tf32 = True
