@@ -5,26 +5,31 @@
 // samples of 128 queries go straight into the A operand of a tensor-core GEMM
 //   out[b, n, q] = act( sum_k corr[b, k, q] * Wt[n, k] + bias[n] ),   n < Cout <= 256.
 //
-//   CTA     = 128 consecutive queries of one batch element, all levels; 576 threads:
-//   warps 0-15 gather + resample exactly like lookup_tma_kernel (one TMA box per (query, level) into the warp's own
-//              slots, 4 lanes per query, a warp owns 8 queries through all levels), but the samples are rounded to
-//              fp16 and stored into the shared-memory A operand of the level instead of global memory; one mbarrier
-//              per level tells the MMA warp that its K range is complete.  Afterwards the same warps are the
-//              epilogue: tcgen05.ld (lane = query), bias, ReLU, 128-byte coalesced stores of out[b, n, q..q+31].
-//   warp 16    producer of the packed weights (B operand): one bulk copy per level.
-//   warp 17    tcgen05.mma.kind::f16 issuer (M = 128, N = Cout, K = 16), fp32 accumulator in tensor memory; the
-//              MMAs of level l run while the other warps resample level l + 1.
-// Both operands use the un-swizzled K-major core-matrix layout ([K/8][rows][8 halfs], 16-byte rows): the K extent of
-// a level (96 or 64) is then free of the 64-element swizzle atom, the A operand needs two level buffers (48 KB)
-// instead of the whole K range (96 KB), and the 8 queries of a warp write 128 contiguous bytes per word.  What is
-// saved goes to the gather ring: 16 warps x 8 KB in flight, which is what bounds this kernel (HBM latency).
-// K layout (private to this kernel; pack_convc1_kernel permutes the weights to match): inside a level entry
-// b*RP + a holds window sample (dx = a - r, dy = b - r), i.e. reference channel l*(2r+1)^2 + a*(2r+1) + b; RP = 2r+2
-// pads a window row to whole 32-bit words, KL rounds the level to a multiple of 16.  Padding entries are written as
-// zeros on the A side and are zero in the packed weights.
+// The GEMM is issued transposed, out^T[n, q] = W[n, k] * S[q, k]^T, so that the WEIGHTS are the tensor-memory (A)
+// operand: they are loaded into tensor memory once per CTA and stay there for the whole persistent kernel, and the
+// shared memory a streamed weight operand would need goes to the gather ring instead.
+//   CTA     = persistent, one per SM; a tile = 64 consecutive queries of one batch element, all levels; 416 threads:
+//   warps 0-7  gather + resample exactly like lookup_tma_kernel (one TMA box per (query, level), 4 lanes per query;
+//              a warp owns 8 queries of the tile), but the samples are rounded to fp16 and stored into the level's
+//              shared-memory B operand S[64 queries][KL] instead of global memory.  Every warp keeps three gathers
+//              in flight (three slot sets, ~190 KB per SM) across levels and tiles; one mbarrier per level tells the
+//              MMA warp that S is complete.
+//   warps 8-11 load the packed weights into tensor memory at start (tcgen05.st, lane = output channel), then run
+//              the epilogue: tcgen05.ld (lane = output channel, registers = 32 consecutive queries), bias, ReLU,
+//              128 contiguous bytes of out[b, n, q..q+31] per thread.
+//   warp 12    tcgen05.mma.kind::f16 issuer (A from tensor memory, M = 128 channels per block, N = 64 queries,
+//              K = 16), fp32 accumulator in tensor memory; the MMAs of level l run while the other warps resample
+//              level l + 1.  Tensor memory: Cout/128 blocks x (K/2 weight columns + 64 accumulator columns) <= 512.
+// S uses the un-swizzled K-major core-matrix layout ([K/8][64 rows][8 halfs]): the K extent of a level (96 or 64)
+// is then free of the 64-element swizzle atom and the 8 queries of a warp write 128 contiguous bytes per word.
+// K layout (private to this kernel; pack_convc1_kernel permutes the weights to match): level l owns entries
+// [l*KL, (l+1)*KL); inside a level entry b*RP + a holds window sample (dx = a - r, dy = b - r), i.e. reference channel
+// l*(2r+1)^2 + a*(2r+1) + b; RP = 2r+2 pads a window row to whole 32-bit words, KL rounds the level to a multiple
+// of 16.  Padding entries are written as zeros on the S side and are zero in the packed weights.
 // Arithmetic: fp16 operands (11-bit significands, the class of the TF32 convolution cuDNN runs for the reference
 // by default), fp32 accumulation.  fp32 pyramids only.
 #include <cstdlib>
+#include <cstring>
 
 #include "lookup_common.cuh"
 #include "rcb_common.cuh"
@@ -40,23 +45,22 @@ struct Cfg {
   static constexpr int RD = G::RD;
   static constexpr int RP = RD + 1;                        // window row padded to an even number of halfs
   static constexpr int KL = (RD * RP + 15) / 16 * 16;      // K entries per level: 96 (r = 4), 64 (r = 3)
-  static constexpr int BM = 128;
-  static constexpr int MATH_WARPS = 8;                     // two groups of 8 queries each
-  static constexpr int EPI_WARPS = 4;                       // one per tensor-memory lane quarter
-  static constexpr int THREADS = 32 * (MATH_WARPS + EPI_WARPS + 2);
+  static constexpr int BQ = 64;                            // queries per tile = N of the MMA
+  static constexpr int GROUPS = BQ / 8;                    // query groups of 8
+  static constexpr int MATH_WARPS = 2 * GROUPS;            // two warps alternate on the chunks of a group
+  static constexpr int EPI_WARPS = 4;                      // one per tensor-memory lane quarter
+  static constexpr int THREADS = 32 * (MATH_WARPS + EPI_WARPS + 1);
+  static constexpr int NSLOT = 3;                          // gathers in flight per query group
   static constexpr int SLOT_BYTES = G::SLOT_BYTES;
   static constexpr int WARP_RING = 8 * SLOT_BYTES;
-  static constexpr int MAX_N = 256;
-  static constexpr int A_LBO = BM * 16;                    // bytes between K chunks of 8: [K/8][128 rows][16 B]
-  static constexpr int A_BUF_BYTES = (KL / 8) * A_LBO;     // one level
-  static constexpr int B_BYTES = (KL / 8) * MAX_N * 16;    // one level of weights: [K/8][N][16 B]
-  static constexpr int OFF_B = 2 * A_BUF_BYTES;
-  static constexpr int OFF_RING = OFF_B + B_BYTES;
-  static constexpr int OFF_BIAS = OFF_RING + 2 * MATH_WARPS * WARP_RING;
-  static constexpr int OFF_BAR = OFF_BIAS + MAX_N * 4;
-  // barriers: gather[2 per warp], level_done[4], a_free[2], acc_full[2], d_free[2], b_full[2], b_empty[2], then the
-  // tensor-memory slot
-  static constexpr int NBAR = 2 * MATH_WARPS + RCB_MAX_LEVELS + 10;
+  static constexpr int S_LBO = BQ * 16;                    // bytes between K chunks of 8: [K/8][64 rows][16 B]
+  static constexpr int S_BUF_BYTES = (KL / 8) * S_LBO;     // one level
+  static constexpr int OFF_RING = 2 * S_BUF_BYTES;
+  static constexpr int STAGE_BYTES = 32 * 64;              // epilogue staging per warp: 32 channels x 16 queries
+  static constexpr int OFF_STAGE = OFF_RING + GROUPS * NSLOT * WARP_RING;
+  static constexpr int OFF_BAR = OFF_STAGE + EPI_WARPS * STAGE_BYTES;
+  // barriers: gather[NSLOT per group], level_done[4], s_free[2], acc_full, d_free, w_full, then the tensor-memory slot
+  static constexpr int NBAR = GROUPS * NSLOT + RCB_MAX_LEVELS + 5;
   static constexpr int SMEM_BYTES = OFF_BAR + 8 * NBAR + 16;
   static constexpr int SMEM_ALLOC = SMEM_BYTES + 128;      // the base is rounded up to 128 bytes (TMA destinations)
 };
@@ -68,21 +72,15 @@ RCB_DEVINL uint64_t make_desc_interleaved(uint32_t addr, uint32_t lbo, uint32_t 
          ((uint64_t)1 << 46);
 }
 
-RCB_DEVINL void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
-               : "memory");
-}
-
 template <int R>
 __global__ void __launch_bounds__(Cfg<R>::THREADS, 1)
-lookup_conv_kernel(const __grid_constant__ LookupMaps maps, PyramidDev pyr, const float* __restrict__ coords,
+lookup_conv_kernel(const __grid_constant__ LookupMaps maps, const __grid_constant__ CUtensorMap omap, PyramidDev pyr, const float* __restrict__ coords,
                    const __half* __restrict__ wpack, const float* __restrict__ bias, float* __restrict__ out, int Q,
-                   int L, int N, int relu, int tiles_q, int ntiles, int dbg) {
+                   int L, int N, int relu, int tiles_q, int ntiles, int tmem_cols, int use_tma_store, int dbg, unsigned long long* prof) {
   using C = Cfg<R>;
   using G = typename C::G;
   constexpr int RD = C::RD, RP = C::RP, KL = C::KL, ROWS = G::ROWS, NMIN = G::NMIN, NMAX = G::NMAX;
-  constexpr int NBMAX = G::NBMAX, MW = C::MATH_WARPS;
+  constexpr int NBMAX = G::NBMAX, MW = C::MATH_WARPS, NG = C::GROUPS, NS = C::NSLOT, BQ = C::BQ;
   extern __shared__ unsigned char smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 127u) & ~127u;
@@ -90,174 +88,237 @@ lookup_conv_kernel(const __grid_constant__ LookupMaps maps, PyramidDev pyr, cons
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t bar0 = base + C::OFF_BAR;
-  auto gbar = [&](int w) { return bar0 + 8 * w; };
-  auto level_done = [&](int l) { return bar0 + 8 * (2 * MW + l); };
-  auto a_free = [&](int i) { return bar0 + 8 * (2 * MW + RCB_MAX_LEVELS + i); };
-  auto acc_full = [&](int d) { return bar0 + 8 * (2 * MW + RCB_MAX_LEVELS + 2 + d); };
-  auto d_free = [&](int d) { return bar0 + 8 * (2 * MW + RCB_MAX_LEVELS + 4 + d); };
-  auto b_full = [&](int i) { return bar0 + 8 * (2 * MW + RCB_MAX_LEVELS + 6 + i); };
-  auto b_empty = [&](int i) { return bar0 + 8 * (2 * MW + RCB_MAX_LEVELS + 8 + i); };
-  constexpr int EW0 = MW, PW = MW + C::EPI_WARPS, TW = MW + C::EPI_WARPS + 1;  // first epilogue / producer / MMA warp
+  auto gbar = [&](int i) { return bar0 + 8 * i; };
+  auto level_done = [&](int l) { return bar0 + 8 * (NG * NS + l); };
+  auto s_free = [&](int i) { return bar0 + 8 * (NG * NS + RCB_MAX_LEVELS + i); };
+  const uint32_t acc_full = bar0 + 8 * (NG * NS + RCB_MAX_LEVELS + 2);
+  const uint32_t d_free = acc_full + 8;
+  const uint32_t w_full = acc_full + 16;
   const uint32_t tmem_slot = bar0 + 8 * C::NBAR;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + C::OFF_BAR + 8 * C::NBAR);
-  float* sbias = reinterpret_cast<float*>(smem + C::OFF_BIAS);
+  constexpr int EW0 = MW, TW = MW + C::EPI_WARPS;  // first epilogue warp, MMA warp
 
   if (tid == 0) {
-    for (int w = 0; w < 2 * MW; ++w) mbar_init(gbar(w), 8);
-    for (int l = 0; l < RCB_MAX_LEVELS; ++l) mbar_init(level_done(l), MW);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(a_free(i), 1);
-      mbar_init(acc_full(i), 1);
-      mbar_init(d_free(i), C::EPI_WARPS);
-      mbar_init(b_full(i), 1);
-      mbar_init(b_empty(i), 1);
-    }
+    for (int i = 0; i < NG * NS; ++i) mbar_init(gbar(i), 8);
+    for (int l = 0; l < RCB_MAX_LEVELS; ++l) mbar_init(level_done(l), NG);
+    mbar_init(s_free(0), 1);
+    mbar_init(s_free(1), 1);
+    mbar_init(acc_full, 1);
+    mbar_init(d_free, C::EPI_WARPS);
+    mbar_init(w_full, MW + C::EPI_WARPS);
     fence_barrier_init();
   }
-  if (tid < N) sbias[tid] = bias ? __ldg(bias + tid) : 0.f;
-  if (warp == TW) tc::tmem_alloc<1>(tmem_slot, 512);  // two accumulators: tile i and tile i + 1
+  if (warp == TW) tc::tmem_alloc<1>(tmem_slot, (uint32_t)tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
   const int tile0 = blockIdx.x, tstep = gridDim.x;
+  const int nmb = (N + 127) >> 7;        // 128-channel blocks
+  const int KW = (L * KL) >> 1;          // 32-bit weight columns per block
+  const uint32_t d_col0 = (uint32_t)(nmb * KW);
 
-  if (warp == PW) {
-    // ---- weight producer: half a level's [KL/16][N][8] fp16 block per bulk copy, two buffers, so the weights of a
-    // level are resident before its samples are and the MMAs start the moment the level completes ----
-    const uint32_t bytes = (uint32_t)(KL / 2 * N * 2);
-    int c = 0;
-    for (int tile = tile0; tile < ntiles; tile += tstep) {
-      for (int l2 = 0; l2 < 2 * L; ++l2, ++c) {
-        mbar_wait(b_empty(c & 1), (uint32_t)(((c >> 1) & 1) ^ 1));
+  // weights -> tensor memory, once per CTA: lane = output channel; the five warps of a lane quarter (four resampling
+  // warps and one epilogue warp) share the 32-column chunks of its rows
+  auto load_weights = [&]() {
+    const int quarter = warp & 3, part = warp >> 2;
+    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+    const int nchunk = (KW + 31) >> 5;
+    for (int idx = part; idx < nmb * nchunk; idx += (MW + C::EPI_WARPS) / 4) {
+      const int mb = idx / nchunk, ch = idx % nchunk;
+      const uint4* row = reinterpret_cast<const uint4*>(wpack + (long long)(mb * 128 + quarter * 32 + lane) * (2 * KW));
+      uint32_t r[32];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (ch * 32 + 4 * k < KW) v = __ldg(row + ch * 8 + k);
+        r[4 * k + 0] = v.x; r[4 * k + 1] = v.y; r[4 * k + 2] = v.z; r[4 * k + 3] = v.w;
+      }
+      if (ch * 32 + 32 <= KW) {
+        tc::tmem_st32(tmem_base + lane_base + mb * KW + ch * 32, r);
+      } else {  // last partial chunk of a row: 16 columns
+        asm volatile(
+            "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+            "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+            ::"r"(tmem_base + lane_base + mb * KW + ch * 32), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]),
+              "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]),
+              "r"(r[14]), "r"(r[15])
+            : "memory");
+      }
+    }
+    tc::tmem_st_wait();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(w_full);
+  };
+
+  if (warp == TW) {
+    // ---- MMA issuer: per level and channel block KL/16 K steps, as soon as the level's samples are in place ----
+    const uint32_t idesc = tc::make_idesc_f16_mn(128, BQ);
+    long long w_lv = 0, w_df = 0, w_wf = 0;
+    long long* pw = prof ? &w_lv : nullptr;
+    const long long clk0 = clock64();
+    mbar_wait_t(w_full, 0, prof ? &w_wf : nullptr);
+    tc_fence_after();
+    int g = 0, i = 0;
+    for (int tile = tile0; tile < ntiles; tile += tstep, ++i) {
+      if (i >= 1) mbar_wait_t(d_free, (uint32_t)((i - 1) & 1), prof ? &w_df : nullptr);  // previous tile's epilogue has read it
+      for (int l = 0; l < L; ++l, ++g) {
+        mbar_wait_t(level_done(l), (uint32_t)(i & 1), pw);
+        tc_fence_after();
         if (elect_one()) {
-          mbar_expect_tx(b_full(c & 1), bytes);
-          bulk_load(base + C::OFF_B + (c & 1) * (C::B_BYTES / 2), wpack + (long long)l2 * (KL / 2) * N, bytes,
-                    b_full(c & 1));
+          const uint32_t s_addr = base + (g & 1) * C::S_BUF_BYTES;
+          for (int mb = 0; mb < nmb; ++mb) {
+#pragma unroll
+            for (int t = 0; t < KL / 16; ++t) {
+              if (dbg & 1) break;  // timing experiment: no MMAs
+              const uint64_t sdesc = make_desc_interleaved(s_addr + t * 2 * C::S_LBO, C::S_LBO, 128);
+              tc::umma_bf16_ts<1>(tmem_base + d_col0 + mb * BQ, tmem_base + mb * KW + l * (KL / 2) + t * 8, sdesc, idesc,
+                                  (l > 0 || t > 0) ? 1u : 0u);
+            }
+          }
+          tc::umma_commit<1>(s_free(g & 1));
+          if (l == L - 1) tc::umma_commit<1>(acc_full);
         }
         __syncwarp();
       }
     }
-  } else if (warp == TW) {
-    // ---- MMA issuer: KL/16 K steps per level as soon as the level's samples are in place ----
-    const uint32_t idesc = tc::make_idesc_f16_mn(C::BM, N);
-    int g = 0, i = 0, c = 0;
-    for (int tile = tile0; tile < ntiles; tile += tstep, ++i) {
-      const int d = i & 1;
-      if (i >= 2) mbar_wait(d_free(d), (uint32_t)(((i >> 1) - 1) & 1));  // the epilogue of tile i - 2 has read it
-      for (int l = 0; l < L; ++l, ++g) {
-        mbar_wait(level_done(l), (uint32_t)(i & 1));
-#pragma unroll
-        for (int hf = 0; hf < 2; ++hf, ++c) {
-          mbar_wait(b_full(c & 1), (uint32_t)((c >> 1) & 1));
-          tc_fence_after();
-          if (elect_one()) {
-            const uint32_t a_addr = base + (g & 1) * C::A_BUF_BYTES + hf * (KL / 16) * C::A_LBO;
-            const uint32_t b_addr = base + C::OFF_B + (c & 1) * (C::B_BYTES / 2);
-#pragma unroll
-            for (int t = 0; t < KL / 32; ++t) {
-              if (dbg & 1) break;  // timing experiment: no MMAs
-              const uint64_t adesc = make_desc_interleaved(a_addr + t * 2 * C::A_LBO, C::A_LBO, 128);
-              const uint64_t bdesc = make_desc_interleaved(b_addr + t * 2 * N * 16, (uint32_t)N * 16, 128);
-              tc::umma_bf16_ss(tmem_base + 256 * d, adesc, bdesc, idesc, (l > 0 || hf > 0 || t > 0) ? 1u : 0u);
-            }
-            tc::umma_commit<1>(b_empty(c & 1));
-            if (hf == 1) {
-              tc::umma_commit<1>(a_free(g & 1));
-              if (l == L - 1) tc::umma_commit<1>(acc_full(d));
-            }
-          }
-          __syncwarp();
-        }
-      }
+    if (prof && lane == 0) {
+      atomicAdd(prof + 5, (unsigned long long)(clock64() - clk0));
+      atomicAdd(prof + 6, (unsigned long long)w_lv);
+      atomicAdd(prof + 7, (unsigned long long)w_df);
+      atomicAdd(prof + 8, (unsigned long long)w_wf);
     }
   } else if (warp >= EW0) {
-    // ---- epilogue: lane = query, registers = output channels; bias, ReLU, 128-byte coalesced stores ----
+    // ---- weights -> tensor memory (once), then the epilogue of every tile ----
     const int quarter = warp & 3;
+    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+    long long w_acc = 0;
+    const long long clk0 = clock64();
+    load_weights();
+    const long long clk1 = clock64();
     int i = 0;
     for (int tile = tile0; tile < ntiles; tile += tstep, ++i) {
-      const int d = i & 1;
-      const int bb = tile / tiles_q, qe = (tile % tiles_q) * C::BM + quarter * 32 + lane;
-      mbar_wait(acc_full(d), (uint32_t)((i >> 1) & 1));
+      const int bb = tile / tiles_q, qt = (tile % tiles_q) * BQ;
+      mbar_wait_t(acc_full, (uint32_t)(i & 1), prof ? &w_acc : nullptr);
       tc_fence_after();
-      float* o = out + (long long)bb * N * Q + qe;
-      for (int n0 = 0; n0 < N; n0 += 32) {
-        float v[32];
-        tc::tmem_ld32(tmem_base + 256 * d + ((uint32_t)(quarter * 32) << 16) + n0, v);
-        if (n0 + 32 >= N) {  // the accumulator may be overwritten by the MMAs of tile i + 2
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(d_free(d));
-        }
-        if (qe < Q && !(dbg & 8)) {
+      for (int mb = 0; mb < nmb; ++mb) {
+        const int n = mb * 128 + quarter * 32 + lane;  // this lane's output channel
+        const float bv = (bias && n < N) ? __ldg(bias + n) : 0.f;
+        float* o = out + ((long long)bb * N + n) * Q + qt;
+#pragma unroll
+        for (int c = 0; c < BQ / 32; ++c) {
+          float v[32];
+          tc::tmem_ld32(tmem_base + lane_base + d_col0 + mb * BQ + c * 32, v);
+          if (mb == nmb - 1 && c == BQ / 32 - 1) {  // the accumulator may be overwritten by the next tile's MMAs
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(d_free);
+          }
 #pragma unroll
           for (int k = 0; k < 32; ++k) {
-            if (n0 + k < N) {
-              float x = v[k] + sbias[n0 + k];
-              if (relu) x = fmaxf(x, 0.f);
-              o[(long long)(n0 + k) * Q] = x;
+            v[k] += bv;
+            if (relu) v[k] = fmaxf(v[k], 0.f);
+          }
+          const int q = qt + c * 32;
+          if (dbg & 8) continue;
+          if (use_tma_store) {
+            // 32 channels x 16 queries at a time through a SWIZZLE_64B staging tile and one TMA store, which also
+            // clips queries >= Q and channels >= N
+            unsigned char* stage = smem + C::OFF_STAGE + (warp - EW0) * C::STAGE_BYTES;
+#pragma unroll
+            for (int hq = 0; hq < 2; ++hq) {
+              if (lane == 0) tma_store_wait_read<0>();  // the previous store has read the staging tile
+              __syncwarp();
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                *reinterpret_cast<float4*>(stage + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) =
+                    make_float4(v[hq * 16 + 4 * j], v[hq * 16 + 4 * j + 1], v[hq * 16 + 4 * j + 2], v[hq * 16 + 4 * j + 3]);
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0 && mb * 128 + quarter * 32 < N) {
+                tma_store_3d(&omap, base + C::OFF_STAGE + (warp - EW0) * C::STAGE_BYTES, q + hq * 16,
+                             mb * 128 + quarter * 32, bb);
+                tma_store_commit();
+              }
             }
+          } else if (n < N) {
+#pragma unroll
+            for (int k = 0; k < 32; ++k)
+              if (q + k < Q) o[c * 32 + k] = v[k];
           }
         }
       }
     }
+    if (lane == 0) tma_store_wait_all();
+    if (prof && lane == 0) {
+      atomicAdd(prof + 9, (unsigned long long)(clock64() - clk0));
+      atomicAdd(prof + 10, (unsigned long long)w_acc);
+      atomicAdd(prof + 12, (unsigned long long)(clk1 - clk0));
+    }
   } else {
-    // ---- gather + resample into the level's A operand ----
-    // A warp owns two groups of 8 queries (h = 0, 1), each with its own slots and mbarrier: while it resamples one
-    // group, the gather of the other is in flight, and every finished chunk immediately issues the gather of the
-    // same group's next level (or of the next tile's first level).
+    // ---- gather + resample into the level's S operand ----
+    // A group of 8 queries has one chunk stream (tile, level) and three slot sets: chunk c lives in slot set c % 3.
+    // Two warps alternate on the stream (warp parity = chunk parity); whoever finishes chunk c issues the gather of
+    // chunk c + 3 into the slot set it has just emptied, so three gathers per group stay in flight.
     const int ql = lane >> 2, sub = lane & 3;
+    const int grp = warp >> 1, par = warp & 1;
+    const int m = grp * 8 + ql;  // query row inside the tile
     const int b0 = (RD * sub) >> 2, nb = ((RD * (sub + 1)) >> 2) - b0;  // output rows [b0, b0 + nb), nb <= NBMAX
+    const int my_tiles = tile0 < ntiles ? (ntiles - tile0 + tstep - 1) / tstep : 0;
+    const int nch = my_tiles * L;  // chunks of the group's stream; chunk c is also the CTA's global level counter
 
     struct Pending {
       LevelCoord lc;
       int Hl, Wl;
       bool ok;
     };
-    auto load_coords = [&](int tile, int h, float& cx, float& cy) {
-      const int bb = tile / tiles_q, q = (tile % tiles_q) * C::BM + (warp + MW * h) * 8 + ql;
+    auto load_coords = [&](int tile, float& cx, float& cy) {
+      const int bb = tile / tiles_q, q = (tile % tiles_q) * BQ + m;
       cx = cy = -1.0e6f;
       if (tile < ntiles && q < Q) {
         cx = __ldg(coords + (long long)(bb * 2 + 0) * Q + q);
         cy = __ldg(coords + (long long)(bb * 2 + 1) * Q + q);
       }
     };
-    auto issue = [&](int tile, int l, int h, float cx, float cy) {
+    auto describe = [&](int tile, int l, float cx, float cy) {
       Pending p;
-      const int bb = tile / tiles_q, q = (tile % tiles_q) * C::BM + (warp + MW * h) * 8 + ql;
-      p.ok = q < Q;
+      p.ok = (tile % tiles_q) * BQ + m < Q;
       p.Hl = l == 0 ? pyr.H[0] : l == 1 ? pyr.H[1] : l == 2 ? pyr.H[2] : pyr.H[3];
       p.Wl = l == 0 ? pyr.W[0] : l == 1 ? pyr.W[1] : l == 2 ? pyr.W[2] : pyr.W[3];
       p.lc = level_coord<R>(cx, cy, l, p.Hl, p.Wl);
+      return p;
+    };
+    auto issue = [&](int tile, int l, int slot, float cx, float cy) {
+      const Pending p = describe(tile, l, cx, cy);
       if (sub == 0) {
-        const uint32_t bar = gbar(2 * warp + h);
+        const int bb = tile / tiles_q, q = (tile % tiles_q) * BQ + m;
+        const uint32_t bar = gbar(grp * NS + slot);
         if (p.ok && !(dbg & 2)) {
           const int nx = ((p.lc.xs & 3) + ROWS + 3) >> 2, ny = ((p.lc.ys & 3) + ROWS + 3) >> 2;
           mbar_expect_tx(bar, (uint32_t)(nx * ny * 64));
-          tma_load_3d(base + C::OFF_RING + (2 * warp + h) * C::WARP_RING + ql * C::SLOT_BYTES,
+          tma_load_3d(base + C::OFF_RING + (grp * NS + slot) * C::WARP_RING + ql * C::SLOT_BYTES,
                       &maps.m[l * 4 + (ny - NMIN) * 2 + (nx - NMIN)], bar, (p.lc.xs >> 2) * 16, p.lc.ys >> 2,
                       bb * Q + q);
         } else {
           mbar_arrive(bar);
         }
       }
-      return p;
     };
-    // resamples the gathered windows of group h and writes them into rows of A buffer `abuf`
-    auto consume = [&](const Pending& cur, int h, int abuf) {
+    // resamples the gathered windows in slot set `slot` and writes them into rows of S buffer `sbuf`
+    auto consume = [&](const Pending& cur, int slot, int sbuf) {
       if (!cur.ok || (dbg & 4)) return;
-      const float4* slot =
-          reinterpret_cast<const float4*>(smem + C::OFF_RING + (2 * warp + h) * C::WARP_RING + ql * C::SLOT_BYTES);
-      const int m = (warp + MW * h) * 8 + ql;  // row of the A tile
+      const float4* win =
+          reinterpret_cast<const float4*>(smem + C::OFF_RING + (grp * NS + slot) * C::WARP_RING + ql * C::SLOT_BYTES);
       const LevelCoord lc = cur.lc;
       const int Hl = cur.Hl, Wl = cur.Wl;
       const int ph = lc.xs & 3, py = lc.ys & 3;
       const int nx = (ph + ROWS + 3) >> 2;
       const float fx = lc.fx, fy = lc.fy, gx = 1.0f - lc.fx, gy = 1.0f - lc.fy;
       const bool ragged_w = (Wl & 3) != 0;
-      unsigned char* arow = smem + abuf * C::A_BUF_BYTES + m * 16;
-      auto a_store = [&](int kbyte, uint32_t v) {  // kbyte: byte offset inside the level's K row, multiple of 4
-        *reinterpret_cast<uint32_t*>(arow + (kbyte >> 4) * C::A_LBO + (kbyte & 15)) = v;
+      unsigned char* srow = smem + sbuf * C::S_BUF_BYTES + m * 16;
+      auto s_store = [&](int kbyte, uint32_t v) {  // kbyte: byte offset inside the level's K row, multiple of 4
+        *reinterpret_cast<uint32_t*>(srow + (kbyte >> 4) * C::S_LBO + (kbyte & 15)) = v;
       };
       float hp[RD];
 #pragma unroll
@@ -266,7 +327,7 @@ lookup_conv_kernel(const __grid_constant__ LookupMaps maps, PyramidDev pyr, cons
         const int j = b0 + jj;  // window row
         const int ya = py + j;  // row inside the fetched box
         const bool row_ok = lc.ys + j < Hl;
-        const float4* rowp = slot + ((ya >> 2) * nx) * 4 + (ya & 3);
+        const float4* rowp = win + ((ya >> 2) * nx) * 4 + (ya & 3);
         float w[4 * NMAX];
 #pragma unroll
         for (int k = 0; k < NMAX; ++k) {
@@ -295,7 +356,7 @@ lookup_conv_kernel(const __grid_constant__ LookupMaps maps, PyramidDev pyr, cons
             const float o0 = gy * hp[2 * a2] + fy * hh[2 * a2];
             const float o1 = (2 * a2 + 1 < RD) ? gy * hp[(2 * a2 + 1) % RD] + fy * hh[(2 * a2 + 1) % RD] : 0.f;
             const __half2 hv = __floats2half2_rn(o0, o1);
-            a_store(kb + 4 * a2, *reinterpret_cast<const uint32_t*>(&hv));
+            s_store(kb + 4 * a2, *reinterpret_cast<const uint32_t*>(&hv));
           }
         }
 #pragma unroll
@@ -303,43 +364,61 @@ lookup_conv_kernel(const __grid_constant__ LookupMaps maps, PyramidDev pyr, cons
       }
       if (sub == 3) {  // the level's trailing K padding must be finite: zeros
 #pragma unroll
-        for (int k = 0; k < (KL - RD * RP) / 2; ++k) a_store(RD * RP * 2 + 4 * k, 0u);
+        for (int k = 0; k < (KL - RD * RP) / 2; ++k) s_store(RD * RP * 2 + 4 * k, 0u);
       }
     };
-    float cx0, cy0, cx1, cy1, cxn0, cyn0, cxn1, cyn1;
-    load_coords(tile0, 0, cx0, cy0);
-    load_coords(tile0, 1, cx1, cy1);
-    Pending pend0 = issue(tile0, 0, 0, cx0, cy0);
-    Pending pend1 = issue(tile0, 0, 1, cx1, cy1);
-    int cnt = 0, g = 0;
-    for (int tile = tile0; tile < ntiles; tile += tstep) {
-      const int next_tile = tile + tstep;
-      load_coords(next_tile, 0, cxn0, cyn0);
-      load_coords(next_tile, 1, cxn1, cyn1);
-      for (int l = 0; l < L; ++l, ++g, ++cnt) {
-        if (g >= 2) mbar_wait(a_free(g & 1), (uint32_t)(((g >> 1) - 1) & 1));  // the MMAs two levels back have read it
-        // group 0
-        mbar_wait(gbar(2 * warp), (uint32_t)(cnt & 1));
-        consume(pend0, 0, g & 1);
-        __syncwarp();  // every lane is done with the slots before the next gather lands in them
-        if (l + 1 < L) {
-          pend0 = issue(tile, l + 1, 0, cx0, cy0);
-        } else if (next_tile < ntiles) {
-          pend0 = issue(next_tile, 0, 0, cxn0, cyn0);
-        }
-        // group 1
-        mbar_wait(gbar(2 * warp + 1), (uint32_t)(cnt & 1));
-        consume(pend1, 1, g & 1);
-        fence_proxy_async_smem();  // A writes (both groups) -> visible to the tensor core's reads
-        __syncwarp();
-        if (lane == 0) mbar_arrive(level_done(l));
-        if (l + 1 < L) {
-          pend1 = issue(tile, l + 1, 1, cx1, cy1);
-        } else if (next_tile < ntiles) {
-          pend1 = issue(next_tile, 0, 1, cxn1, cyn1);
-        }
+
+    // Cursors over the group's stream.  The consume cursor visits this warp's chunks (c = par, par + 2, ...); the
+    // issue cursor runs three chunks ahead of it.  Both keep the coordinates of their tile and prefetch the next.
+    long long w_g = 0, w_s = 0, t_c = 0, t_f = 0, t_i = 0;
+    const long long clk0 = clock64();
+    int ct = tile0, cl = par, it = tile0, il = par + NS;  // (tile, level) of chunk c and of chunk c + 3
+    while (cl >= L) { cl -= L; ct += tstep; }
+    while (il >= L) { il -= L; it += tstep; }
+    float ccx, ccy, cnx, cny, icx, icy, inx, iny;
+    load_coords(ct, ccx, ccy);
+    load_coords(ct + tstep, cnx, cny);
+    load_coords(it, icx, icy);
+    load_coords(it + tstep, inx, iny);
+    if (par == 0) {  // prologue: chunks 0, 1, 2 of the stream
+      int pt = tile0, pl = 0;
+      float px, py_;
+      load_coords(pt, px, py_);
+      for (int c = 0; c < NS && c < nch; ++c) {
+        issue(pt, pl, c, px, py_);
+        if (++pl == L) { pl = 0; pt += tstep; load_coords(pt, px, py_); }
       }
-      cx0 = cxn0; cy0 = cyn0; cx1 = cxn1; cy1 = cyn1;
+    }
+    load_weights();  // while the first gathers are in flight
+    for (int c = par; c < nch; c += 2) {
+      const int slot = c % NS;
+      const Pending cur = describe(ct, cl, ccx, ccy);
+      if (c >= 2) mbar_wait_t(s_free(c & 1), (uint32_t)(((c >> 1) - 1) & 1), prof ? &w_s : nullptr);  // MMAs two levels back
+      mbar_wait_t(gbar(grp * NS + slot), (uint32_t)((c / NS) & 1), prof ? &w_g : nullptr);
+      const long long tc0 = prof ? clock64() : 0;
+      consume(cur, slot, c & 1);
+      const long long tc1 = prof ? clock64() : 0;
+      if (prof) t_c += tc1 - tc0;
+      fence_proxy_async_smem();  // S writes -> visible to the tensor core's reads
+      __syncwarp();              // and every lane is done with the slots before the next gather lands in them
+      if (lane == 0) mbar_arrive(level_done(cl));
+      const long long tc2 = prof ? clock64() : 0;
+      if (c + NS < nch) issue(it, il, slot, icx, icy);
+      if (prof) { t_f += tc2 - tc1; t_i += clock64() - tc2; }
+      // advance both cursors by two chunks
+      cl += 2;
+      if (cl >= L) { cl -= L; ct += tstep; ccx = cnx; ccy = cny; load_coords(ct + tstep, cnx, cny); }
+      il += 2;
+      if (il >= L) { il -= L; it += tstep; icx = inx; icy = iny; load_coords(it + tstep, inx, iny); }
+    }
+    if (prof && lane == 0) {
+      atomicAdd(prof + 0, (unsigned long long)(clock64() - clk0));
+      atomicAdd(prof + 1, (unsigned long long)w_g);
+      atomicAdd(prof + 2, (unsigned long long)w_s);
+      atomicAdd(prof + 3, (unsigned long long)t_c);
+      atomicAdd(prof + 4, (unsigned long long)nch);
+      atomicAdd(prof + 13, (unsigned long long)t_f);
+      atomicAdd(prof + 14, (unsigned long long)t_i);
     }
   }
 
@@ -347,24 +426,23 @@ lookup_conv_kernel(const __grid_constant__ LookupMaps maps, PyramidDev pyr, cons
   __syncthreads();
   if (warp == TW) {
     tc_fence_after();
-    tc::tmem_dealloc<1>(tmem_base, 512);
+    tc::tmem_dealloc<1>(tmem_base, (uint32_t)tmem_cols);
   }
 }
 
-// weight[n][l*RD*RD + a*RD + b] (fp32, the Conv2d weight of convc1 viewed [Cout, Cin]) -> wp[l][k/8][n][k%8] fp16
-// with k = b*RP + a inside the level, zero padded
+// weight[n][l*RD*RD + a*RD + b] (fp32, the Conv2d weight of convc1 viewed [Cout, Cin]) -> wp[n][l*KL + b*RP + a] fp16,
+// rows padded with zeros to a multiple of 128 channels, K padding zero
 __global__ void __launch_bounds__(256)
-pack_convc1_kernel(const float* __restrict__ w, __half* __restrict__ wp, int cout, int L, int RD, int RP, int KL) {
-  const long long n_el = (long long)L * KL * cout;
+pack_convc1_kernel(const float* __restrict__ w, __half* __restrict__ wp, int cout, int npad, int L, int RD, int RP,
+                   int KL) {
+  const int K = L * KL;
+  const long long n_el = (long long)npad * K;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_el; i += (long long)gridDim.x * blockDim.x) {
-    const int e = (int)(i & 7);
-    const int n = (int)((i >> 3) % cout);
-    const int k8 = (int)((i >> 3) / cout % (KL / 8));
-    const int l = (int)(i / ((long long)KL * cout));
-    const int r = k8 * 8 + e;
+    const int n = (int)(i / K), k = (int)(i % K);
+    const int l = k / KL, r = k % KL;
     const int bb = r / RP, a = r % RP;
     float v = 0.f;
-    if (bb < RD && a < RD) v = __ldg(w + (long long)n * (L * RD * RD) + l * RD * RD + a * RD + bb);
+    if (n < cout && bb < RD && a < RD) v = __ldg(w + (long long)n * (L * RD * RD) + l * RD * RD + a * RD + bb);
     wp[i] = __float2half_rn(v);
   }
 }
@@ -381,15 +459,33 @@ template <int R>
 static int launch_r(const LookupPlan& plan, const PyramidDev& pd, const float* coords, const __half* wpack,
                     const float* bias, float* out, int cout, int relu, cudaStream_t s) {
   using C = Cfg<R>;
-  const int Q = plan.H * plan.W;
+  const int Q = plan.H * plan.W, L = plan.lay.levels;
   cudaError_t e = cudaFuncSetAttribute(lookup_conv_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        C::SMEM_ALLOC);
   if (e != cudaSuccess) return (int)e;
-  const int tiles_q = (Q + C::BM - 1) / C::BM, ntiles = tiles_q * plan.B;
+  const int nmb = (cout + 127) / 128;
+  const int need = nmb * (L * C::KL / 2 + C::BQ);  // weight + accumulator columns
+  int tmem_cols = 32;
+  while (tmem_cols < need) tmem_cols *= 2;
+  if (tmem_cols > 512) return RCB_ERR_UNSUPPORTED;
   static const int dbg = getenv("RCB_LCONV_DEBUG") ? atoi(getenv("RCB_LCONV_DEBUG")) : 0;  // timing experiments
+  // output as a [B][N][Q] tensor for the epilogue's TMA stores (needs 16-byte row pitch)
+  CUtensorMap omap;
+  int use_tma_store = (Q % 4 == 0) && encode_fn() != nullptr;
+  if (use_tma_store) {
+    cuuint64_t dims[3] = {(cuuint64_t)Q, (cuuint64_t)cout, (cuuint64_t)plan.B};
+    cuuint64_t str[2] = {(cuuint64_t)Q * 4, (cuuint64_t)Q * 4 * cout};
+    cuuint32_t box[3] = {16, 32, 1};
+    if (!encode(&omap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, out, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B)) use_tma_store = 0;
+  }
+  if (!use_tma_store) memset(&omap, 0, sizeof(omap));
+  const char* pp = getenv("RCB_LCONV_PROF_PTR");  // debug: 16 device uint64 counters supplied by tools/time_lookup_conv.py
+  unsigned long long* prof = pp ? reinterpret_cast<unsigned long long*>(strtoull(pp, nullptr, 0)) : nullptr;
+  const int tiles_q = (Q + C::BQ - 1) / C::BQ, ntiles = tiles_q * plan.B;
   const int grid = ntiles < kNumSMs ? ntiles : kNumSMs;  // persistent: one CTA per SM walks tiles grid apart
-  lookup_conv_kernel<R><<<grid, C::THREADS, C::SMEM_ALLOC, s>>>(plan.maps, pd, coords, wpack, bias, out, Q,
-                                                                 plan.lay.levels, cout, relu, tiles_q, ntiles, dbg);
+  lookup_conv_kernel<R><<<grid, C::THREADS, C::SMEM_ALLOC, s>>>(plan.maps, omap, pd, coords, wpack, bias, out, Q, L,
+                                                                 cout, relu, tiles_q, ntiles, tmem_cols, use_tma_store,
+                                                                 dbg, prof);
   return launch_status();
 }
 
@@ -397,19 +493,20 @@ static int launch_r(const LookupPlan& plan, const PyramidDev& pd, const float* c
 
 size_t convc1_pack_bytes(int cout, int levels, int radius) {
   int rd, rp, kl;
-  if (!lconv::geometry(radius, &rd, &rp, &kl) || cout < 16 || cout > 256 || cout % 16 || levels < 1 ||
+  if (!lconv::geometry(radius, &rd, &rp, &kl) || cout < 16 || cout > 256 || cout % 16 || levels < 2 ||
       levels > RCB_MAX_LEVELS)
     return 0;
-  return (size_t)levels * kl * cout * sizeof(__half);
+  return (size_t)((cout + 127) / 128 * 128) * levels * kl * sizeof(__half);
 }
 
 int launch_convc1_pack(const float* weight, void* wpack, int cout, int levels, int radius, cudaStream_t s) {
   int rd, rp, kl;
   if (!weight || !wpack) return RCB_ERR_INVALID_ARGUMENT;
   if (convc1_pack_bytes(cout, levels, radius) == 0 || !lconv::geometry(radius, &rd, &rp, &kl)) return RCB_ERR_UNSUPPORTED;
-  const long long n_el = (long long)levels * kl * cout;
-  lconv::pack_convc1_kernel<<<(int)((n_el + 255) / 256), 256, 0, s>>>(weight, static_cast<__half*>(wpack), cout, levels,
-                                                                     rd, rp, kl);
+  const int npad = (cout + 127) / 128 * 128;
+  const long long n_el = (long long)npad * levels * kl;
+  lconv::pack_convc1_kernel<<<(int)((n_el + 255) / 256), 256, 0, s>>>(weight, static_cast<__half*>(wpack), cout, npad,
+                                                                     levels, rd, rp, kl);
   return launch_status();
 }
 
@@ -420,7 +517,8 @@ int launch_lookup_convc1(const void* plan_, const float* coords, const void* wpa
   if (plan->lay.dtype != RCB_F32) return RCB_ERR_UNSUPPORTED;
   int rd, rp, kl;
   if (!lconv::geometry(plan->radius, &rd, &rp, &kl) || cout < 16 || cout > 256 || cout % 16) return RCB_ERR_UNSUPPORTED;
-  if (((uintptr_t)wpack & 15) != 0) return RCB_ERR_INVALID_ARGUMENT;
+  if (plan->lay.levels < 2) return RCB_ERR_UNSUPPORTED;  // the per-level barriers need two levels to alternate
+  if (((uintptr_t)wpack & 15) != 0 || ((uintptr_t)out & 15) != 0) return RCB_ERR_INVALID_ARGUMENT;
   const PyramidDev pd = make_pyramid_dev(plan->ptr, plan->lay);
   const __half* wp = static_cast<const __half*>(wpack);
   if (plan->radius == 3) return lconv::launch_r<3>(*plan, pd, coords, wp, bias, out, cout, relu, s);
