@@ -8,18 +8,21 @@
 // The GEMM is issued transposed, out^T[n, q] = W[n, k] * S[q, k]^T, so that the WEIGHTS are the tensor-memory (A)
 // operand: they are loaded into tensor memory once per CTA and stay there for the whole persistent kernel, and the
 // shared memory a streamed weight operand would need goes to the gather ring instead.
-//   CTA     = persistent, one per SM; a tile = 64 consecutive queries of one batch element, all levels; 416 threads:
-//   warps 0-7  gather + resample exactly like lookup_tma_kernel (one TMA box per (query, level), 4 lanes per query;
-//              a warp owns 8 queries of the tile), but the samples are rounded to fp16 and stored into the level's
-//              shared-memory B operand S[64 queries][KL] instead of global memory.  Every warp keeps three gathers
-//              in flight (three slot sets, ~190 KB per SM) across levels and tiles; one mbarrier per level tells the
-//              MMA warp that S is complete.
-//   warps 8-11 load the packed weights into tensor memory at start (tcgen05.st, lane = output channel), then run
-//              the epilogue: tcgen05.ld (lane = output channel, registers = 32 consecutive queries), bias, ReLU,
-//              128 contiguous bytes of out[b, n, q..q+31] per thread.
-//   warp 12    tcgen05.mma.kind::f16 issuer (A from tensor memory, M = 128 channels per block, N = 64 queries,
+//   CTA     = persistent, one per SM; a tile = 64 consecutive queries of one batch element, all levels; 672 threads:
+//   warps 0-15 gather + resample exactly like lookup_tma_kernel (one TMA box per (query, level), 4 lanes per query),
+//              but the samples are rounded to fp16 and stored into the level's shared-memory B operand
+//              S[64 queries][KL] instead of global memory.  The 8 queries of a group form one chunk stream
+//              (tile, level) over three slot sets; two warps alternate on it, and whoever finishes chunk c issues the
+//              gather of chunk c + 3, so three gathers per group (~190 KB per SM) stay in flight across levels and
+//              tiles.  One mbarrier per level tells the MMA warp that S is complete.
+//   warps 16-19 epilogue: tcgen05.ld (lane = output channel, registers = 32 consecutive queries), bias, ReLU, a
+//              SWIZZLE_64B staging tile (32 channels x 16 queries, conflict-free 16-byte stores) and one TMA store per
+//              tile of out[b, n0..n0+31, q..q+15], which also clips the ragged edges; direct stores when the row
+//              pitch is not a multiple of 16 bytes.
+//   warp 20    tcgen05.mma.kind::f16 issuer (A from tensor memory, M = 128 channels per block, N = 64 queries,
 //              K = 16), fp32 accumulator in tensor memory; the MMAs of level l run while the other warps resample
 //              level l + 1.  Tensor memory: Cout/128 blocks x (K/2 weight columns + 64 accumulator columns) <= 512.
+//   All warps of a lane quarter share the one-time copy of the packed weights into tensor memory (tcgen05.st).
 // S uses the un-swizzled K-major core-matrix layout ([K/8][64 rows][8 halfs]): the K extent of a level (96 or 64)
 // is then free of the 64-element swizzle atom and the 8 queries of a warp write 128 contiguous bytes per word.
 // K layout (private to this kernel; pack_convc1_kernel permutes the weights to match): level l owns entries
@@ -72,15 +75,18 @@ RCB_DEVINL uint64_t make_desc_interleaved(uint32_t addr, uint32_t lbo, uint32_t 
          ((uint64_t)1 << 46);
 }
 
-template <int R>
+template <int R, bool PROF>
 __global__ void __launch_bounds__(Cfg<R>::THREADS, 1)
 lookup_conv_kernel(const __grid_constant__ LookupMaps maps, const __grid_constant__ CUtensorMap omap, PyramidDev pyr, const float* __restrict__ coords,
                    const __half* __restrict__ wpack, const float* __restrict__ bias, float* __restrict__ out, int Q,
-                   int L, int N, int relu, int tiles_q, int ntiles, int tmem_cols, int use_tma_store, int dbg, unsigned long long* prof) {
+                   int L, int N, int relu, int tiles_q, int ntiles, int tmem_cols, int use_tma_store, int dbg_, unsigned long long* prof_) {
   using C = Cfg<R>;
   using G = typename C::G;
   constexpr int RD = C::RD, RP = C::RP, KL = C::KL, ROWS = G::ROWS, NMIN = G::NMIN, NMAX = G::NMAX;
   constexpr int NBMAX = G::NBMAX, MW = C::MATH_WARPS, NG = C::GROUPS, NS = C::NSLOT, BQ = C::BQ;
+  // the timing switches and cycle counters exist only in the PROF instantiation (tools/time_lookup_conv.py)
+  const int dbg = PROF ? dbg_ : 0;
+  unsigned long long* const prof = PROF ? prof_ : nullptr;
   extern __shared__ unsigned char smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 127u) & ~127u;
@@ -372,14 +378,6 @@ lookup_conv_kernel(const __grid_constant__ LookupMaps maps, const __grid_constan
     // issue cursor runs three chunks ahead of it.  Both keep the coordinates of their tile and prefetch the next.
     long long w_g = 0, w_s = 0, t_c = 0, t_f = 0, t_i = 0;
     const long long clk0 = clock64();
-    int ct = tile0, cl = par, it = tile0, il = par + NS;  // (tile, level) of chunk c and of chunk c + 3
-    while (cl >= L) { cl -= L; ct += tstep; }
-    while (il >= L) { il -= L; it += tstep; }
-    float ccx, ccy, cnx, cny, icx, icy, inx, iny;
-    load_coords(ct, ccx, ccy);
-    load_coords(ct + tstep, cnx, cny);
-    load_coords(it, icx, icy);
-    load_coords(it + tstep, inx, iny);
     if (par == 0) {  // prologue: chunks 0, 1, 2 of the stream
       int pt = tile0, pl = 0;
       float px, py_;
@@ -390,6 +388,14 @@ lookup_conv_kernel(const __grid_constant__ LookupMaps maps, const __grid_constan
       }
     }
     load_weights();  // while the first gathers are in flight
+    int ct = tile0, cl = par, it = tile0, il = par + NS;  // (tile, level) of chunk c and of chunk c + 3
+    while (cl >= L) { cl -= L; ct += tstep; }
+    while (il >= L) { il -= L; it += tstep; }
+    float ccx, ccy, cnx, cny, icx, icy, inx, iny;
+    load_coords(ct, ccx, ccy);
+    load_coords(ct + tstep, cnx, cny);
+    load_coords(it, icx, icy);
+    load_coords(it + tstep, inx, iny);
     for (int c = par; c < nch; c += 2) {
       const int slot = c % NS;
       const Pending cur = describe(ct, cl, ccx, ccy);
@@ -460,8 +466,10 @@ static int launch_r(const LookupPlan& plan, const PyramidDev& pd, const float* c
                     const float* bias, float* out, int cout, int relu, cudaStream_t s) {
   using C = Cfg<R>;
   const int Q = plan.H * plan.W, L = plan.lay.levels;
-  cudaError_t e = cudaFuncSetAttribute(lookup_conv_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  cudaError_t e = cudaFuncSetAttribute(lookup_conv_kernel<R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        C::SMEM_ALLOC);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(lookup_conv_kernel<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_ALLOC);
   if (e != cudaSuccess) return (int)e;
   const int nmb = (cout + 127) / 128;
   const int need = nmb * (L * C::KL / 2 + C::BQ);  // weight + accumulator columns
@@ -483,9 +491,14 @@ static int launch_r(const LookupPlan& plan, const PyramidDev& pd, const float* c
   unsigned long long* prof = pp ? reinterpret_cast<unsigned long long*>(strtoull(pp, nullptr, 0)) : nullptr;
   const int tiles_q = (Q + C::BQ - 1) / C::BQ, ntiles = tiles_q * plan.B;
   const int grid = ntiles < kNumSMs ? ntiles : kNumSMs;  // persistent: one CTA per SM walks tiles grid apart
-  lookup_conv_kernel<R><<<grid, C::THREADS, C::SMEM_ALLOC, s>>>(plan.maps, omap, pd, coords, wpack, bias, out, Q, L,
-                                                                 cout, relu, tiles_q, ntiles, tmem_cols, use_tma_store,
-                                                                 dbg, prof);
+  if (dbg || prof)
+    lookup_conv_kernel<R, true><<<grid, C::THREADS, C::SMEM_ALLOC, s>>>(plan.maps, omap, pd, coords, wpack, bias, out, Q,
+                                                                       L, cout, relu, tiles_q, ntiles, tmem_cols,
+                                                                       use_tma_store, dbg, prof);
+  else
+    lookup_conv_kernel<R, false><<<grid, C::THREADS, C::SMEM_ALLOC, s>>>(plan.maps, omap, pd, coords, wpack, bias, out,
+                                                                        Q, L, cout, relu, tiles_q, ntiles, tmem_cols,
+                                                                        use_tma_store, 0, nullptr);
   return launch_status();
 }
 

@@ -27,12 +27,14 @@ RCB_DEVINL bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug traps (the launch fails with an error) instead of hanging the GPU.
+// Bounded wait: a protocol bug traps (the launch fails with an error) instead of hanging the GPU.  try_wait itself
+// suspends the thread for a hardware-defined interval, so the loop body runs rarely; the bound is an iteration
+// count, which keeps clock reads and 64-bit compares out of the polling loop.
 RCB_DEVINL void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
+  uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 8000000000LL) __trap();
+    if (++spins > 200000000u) __trap();
   }
 }
 // true on exactly one lane of a fully converged warp; keeps the surrounding values warp-uniform so the
