@@ -298,6 +298,39 @@ def run_ours(args, cfg):
                 "note": "operands rounded to bf16 (2.6e-3 of max-abs), pyramid stored as fp16; "
                         "final-flow EPE delta vs the reference 1e-3 px mean on the demo frames"}
 
+    # ---- next row of the scope table (8f, f1), reported next to the headline: the lookup fused with the motion
+    # encoder's first layer, against this package's lookup followed by the convolution + ReLU the reference runs
+    fused = None
+    if args.pyramid == "f32" and r in (3, 4) and not args.no_fast_mode:
+        import torch.nn.functional as F
+        from raft_optical_flow_b200 import PackedConvC1
+        cout, cin = (256 if r == 4 else 96), L * (2 * r + 1) ** 2
+        gw = torch.Generator(device="cpu").manual_seed(SEED + 1)
+        wgt = (torch.randn(cout, cin, 1, 1, generator=gw) / cin ** 0.5).to(dev)
+        bia = (0.1 * torch.randn(cout, generator=gw)).to(dev)
+        blk = CorrBlock(dev_f[0][0], dev_f[0][1], num_levels=L, radius=r, mode=args.mode)
+        packed = PackedConvC1(wgt, bia, L, r)
+
+        def timed(fn, n=16):
+            for i in range(3):
+                fn(dev_c[i % iters])
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            for i in range(n):
+                fn(dev_c[i % iters])
+            a1.record()
+            torch.cuda.synchronize(dev)
+            return 1e3 * a0.elapsed_time(a1) / n
+
+        t_f = timed(lambda c: blk.lookup_conv(c, packed))
+        t_p = timed(lambda c: F.relu(F.conv2d(blk(c), wgt, bia)))
+        fused = {"kernel": "lookup_conv_kernel", "out_channels": cout, "us_per_launch": t_f,
+                 "unfused_pair_us": t_p,
+                 "note": "corr_fn(coords) + relu(convc1(corr)) (core/raft.py:219, core/update.py:202) in one launch, "
+                         "fp16 tensor-core operands; unfused pair = this package's lookup + torch conv2d (cuDNN, TF32 "
+                         "allowed as in the reference's defaults) + relu"}
+        del blk, packed
+
     # ---- end to end: host buffers in, host result out ------------------------------------------
     run_e2e(max(2, args.warmup))
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -351,6 +384,8 @@ def run_ours(args, cfg):
     }
     if fast:
         line["fast_mode"] = fast
+    if fused:
+        line["fused_lookup_convc1"] = fused
     if world == 1 and not args.no_cpu_baseline:
         from oracle import oracle as orc
         orc.set_num_threads(len(os.sched_getaffinity(0)))
