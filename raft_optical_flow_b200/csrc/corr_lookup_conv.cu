@@ -396,6 +396,7 @@ lookup_conv_kernel(const __grid_constant__ LookupMaps maps, const __grid_constan
     load_coords(ct + tstep, cnx, cny);
     load_coords(it, icx, icy);
     load_coords(it + tstep, inx, iny);
+    const long long clk_loop = clock64();
     for (int c = par; c < nch; c += 2) {
       const int slot = c % NS;
       const Pending cur = describe(ct, cl, ccx, ccy);
@@ -425,6 +426,7 @@ lookup_conv_kernel(const __grid_constant__ LookupMaps maps, const __grid_constan
       atomicAdd(prof + 4, (unsigned long long)nch);
       atomicAdd(prof + 13, (unsigned long long)t_f);
       atomicAdd(prof + 14, (unsigned long long)t_i);
+      atomicAdd(prof + 15, (unsigned long long)(clk_loop - clk0));
     }
   }
 
