@@ -104,3 +104,21 @@ def test_dropin_modules_resolve_like_the_reference_imports():
         sys.path.remove(os.path.join(ROOT, "dropin"))
         for m in ("corr", "alt_cuda_corr"):
             sys.modules.pop(m, None)
+
+
+def test_convc1_pack_size_and_argument_checks(lib):
+    """Host logic of the fused lookup + convc1 entry points (include/raft_corr_b200.h): K is 96 entries per level at
+    r = 4 and 64 at r = 3 (window rows padded to even length, levels to a multiple of 16), rows padded to 128."""
+    assert lib.rcb_corr_convc1_pack_bytes(256, 4, 4) == 256 * 4 * 96 * 2   # BasicMotionEncoder.convc1 (core/update.py:182)
+    assert lib.rcb_corr_convc1_pack_bytes(96, 4, 3) == 128 * 4 * 64 * 2    # SmallMotionEncoder.convc1 (core/update.py:136)
+    assert lib.rcb_corr_convc1_pack_bytes(16, 3, 4) == 128 * 3 * 96 * 2
+    for cout, levels, radius in ((24, 4, 4), (272, 4, 4), (0, 4, 4), (256, 1, 4), (256, 5, 4), (256, 4, 2), (256, 4, 5)):
+        assert lib.rcb_corr_convc1_pack_bytes(cout, levels, radius) == 0
+    buf = (ctypes.c_float * 64)()
+    p = ctypes.addressof(buf)
+    assert lib.rcb_corr_convc1_pack(None, p, 256, 4, 4, None) == -1
+    assert lib.rcb_corr_convc1_pack(p, p, 24, 4, 4, None) == -2
+    assert lib.rcb_corr_lookup_convc1(None, p, p, None, p, 256, 1, None) == -1
+    blob = (ctypes.c_char * (lib.rcb_corr_lookup_plan_bytes() + 64))()
+    plan = (ctypes.addressof(blob) + 63) & ~63
+    assert lib.rcb_corr_lookup_convc1(plan, p, p, None, p, 256, 1, None) == -1  # plan not initialised
