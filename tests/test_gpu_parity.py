@@ -20,6 +20,7 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-4
 GRAD_TOL = 2e-4
 BF16_TOL = 5e-3
+CONVC1_TOL = 1e-3  # fused lookup + convc1: fp16 tensor-core operands (section 9)
 PARITY_MODES = os.environ.get("RCB_TEST_MODES", "fp32,bf16x3").split(",")
 
 
@@ -294,6 +295,40 @@ def test_full_size_properties(rcb, dev, cfg, mode):
     assert ((v12 - v21.T).abs().max() / v12.abs().max()).item() < TOL
 
 
+@pytest.mark.parametrize("mode", PARITY_MODES)
+def test_largest_config_offsets_beyond_32_bits(rcb, dev, mode):
+    """cfg4 of BASELINE.json (1088x1920 -> 136x240, batch 4): 4.26e9 level-0 elements (17 GB), i.e. element offsets
+    past 2^31 and byte offsets past 2^34.  The on-the-fly formulation never stores the volume, so agreement of the two
+    paths on every batch element checks the build's stores and the lookup's gathers at those offsets."""
+    B, C, H, W, r, L = 4, 256, 136, 240, 4, 4
+    rd = 2 * r + 1
+    gen = torch.Generator(device="cpu").manual_seed(4)
+    f1 = (0.75 * torch.randn(B, C, H, W, generator=gen)).to(dev)
+    f2 = (0.75 * torch.randn(B, C, H, W, generator=gen)).to(dev)
+    ys, xs = torch.meshgrid(torch.arange(H, device=dev), torch.arange(W, device=dev), indexing="ij")
+    grid = torch.stack([xs, ys]).float()[None].repeat(B, 1, 1, 1)
+    coords = grid + 6.0 * torch.randn(B, 2, H, W, generator=gen).to(dev)
+    blk = rcb.CorrBlock(f1, f2, num_levels=L, radius=r, mode=mode)
+    assert sum(b.numel() for b in blk._state.pyr.bufs) > 2 ** 32
+    centre = blk(grid)[:, r * rd + r]
+    want = (f1.double() * f2.double()).sum(1) / np.sqrt(C)
+    assert ((centre.double() - want).abs().max() / want.abs().max()).item() < TOL
+    o1 = blk(coords)
+    wgt = (torch.randn(256, L * rd * rd, 1, 1, generator=gen) / 18.0).to(dev)
+    fused = blk.lookup_conv(coords, rcb.PackedConvC1(wgt, None, L, r), relu=False)
+    old_tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        unfused = torch.nn.functional.conv2d(o1, wgt)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old_tf32
+    assert ((fused - unfused).abs().max() / unfused.abs().max()).item() < CONVC1_TOL
+    del blk, fused, unfused
+    o2 = rcb.AlternateCorrBlock(f1, f2, num_levels=L, radius=r)(coords)
+    for b in range(B):
+        assert ((o1[b] - o2[b]).abs().max() / o2[b].abs().max()).item() < TOL, b
+
+
 # ---------------------------------------------------------------------------------------------
 # boundary behaviour
 # ---------------------------------------------------------------------------------------------
@@ -464,8 +499,6 @@ def test_upsample_flow_vs_oracle(rcb, dev, orc, dims):
 # fp16 tensor-core operands, fp32 accumulate -> the stated bound is 1e-3 of max-abs of the fp32 result (measured
 # 3e-4); the reference itself runs this convolution in TF32 (same 11-bit significands) under cuDNN's defaults.
 # ---------------------------------------------------------------------------------------------
-CONVC1_TOL = 1e-3
-
 
 @pytest.mark.parametrize("name", ["convc1_basic", "convc1_small"])
 def test_lookup_convc1_golden(rcb, dev, name):
