@@ -132,12 +132,13 @@ lookup_conv_kernel(const __grid_constant__ LookupMaps maps, const __grid_constan
     const int nchunk = (KW + 31) >> 5;
     for (int idx = part; idx < nmb * nchunk; idx += (MW + C::EPI_WARPS) / 4) {
       const int mb = idx / nchunk, ch = idx % nchunk;
-      const uint4* row = reinterpret_cast<const uint4*>(wpack + (long long)(mb * 128 + quarter * 32 + lane) * (2 * KW));
+      // packed as [chunk][k][128 rows][16 B]: the 32 lanes of one load read 512 contiguous bytes
+      const uint4* src = reinterpret_cast<const uint4*>(wpack) + (long long)idx * 8 * 128 + quarter * 32 + lane;
       uint32_t r[32];
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         uint4 v = make_uint4(0u, 0u, 0u, 0u);
-        if (ch * 32 + 4 * k < KW) v = __ldg(row + ch * 8 + k);
+        if (ch * 32 + 4 * k < KW) v = __ldg(src + k * 128);
         r[4 * k + 0] = v.x; r[4 * k + 1] = v.y; r[4 * k + 2] = v.z; r[4 * k + 3] = v.w;
       }
       if (ch * 32 + 32 <= KW) {
@@ -387,7 +388,9 @@ lookup_conv_kernel(const __grid_constant__ LookupMaps maps, const __grid_constan
         if (++pl == L) { pl = 0; pt += tstep; load_coords(pt, px, py_); }
       }
     }
+    const long long clk_a = clock64();
     load_weights();  // while the first gathers are in flight
+    const long long clk_b = clock64();
     int ct = tile0, cl = par, it = tile0, il = par + NS;  // (tile, level) of chunk c and of chunk c + 3
     while (cl >= L) { cl -= L; ct += tstep; }
     while (il >= L) { il -= L; it += tstep; }
@@ -427,6 +430,8 @@ lookup_conv_kernel(const __grid_constant__ LookupMaps maps, const __grid_constan
       atomicAdd(prof + 13, (unsigned long long)t_f);
       atomicAdd(prof + 14, (unsigned long long)t_i);
       atomicAdd(prof + 15, (unsigned long long)(clk_loop - clk0));
+      atomicAdd(prof + 16, (unsigned long long)(clk_a - clk0));
+      atomicAdd(prof + 17, (unsigned long long)(clk_b - clk_a));
     }
   }
 
@@ -438,19 +443,24 @@ lookup_conv_kernel(const __grid_constant__ LookupMaps maps, const __grid_constan
   }
 }
 
-// weight[n][l*RD*RD + a*RD + b] (fp32, the Conv2d weight of convc1 viewed [Cout, Cin]) -> wp[n][l*KL + b*RP + a] fp16,
-// rows padded with zeros to a multiple of 128 channels, K padding zero
+// weight[n][l*RD*RD + a*RD + b] (fp32, the Conv2d weight of convc1 viewed [Cout, Cin]) -> fp16 in the order the
+// kernel copies it into tensor memory: [128-channel block][32-column chunk][k = 0..7][row 0..127][8 halfs], where
+// the 8 halfs are K entries ch*64 + k*8 + 0..7 of channel block*128 + row and K entry l*KL + b*RP + a is the window
+// sample (a, b) of level l; rows >= Cout, K padding and the tail of a last partial chunk are zero
 __global__ void __launch_bounds__(256)
-pack_convc1_kernel(const float* __restrict__ w, __half* __restrict__ wp, int cout, int npad, int L, int RD, int RP,
-                   int KL) {
+pack_convc1_kernel(const float* __restrict__ w, __half* __restrict__ wp, int cout, int nmb, int nchunk, int L, int RD,
+                   int RP, int KL) {
   const int K = L * KL;
-  const long long n_el = (long long)npad * K;
+  const long long n_el = (long long)nmb * nchunk * 8 * 128 * 8;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_el; i += (long long)gridDim.x * blockDim.x) {
-    const int n = (int)(i / K), k = (int)(i % K);
-    const int l = k / KL, r = k % KL;
+    const int e = (int)(i & 7), rr = (int)((i >> 3) & 127), k8 = (int)((i >> 10) & 7);
+    const int chunk = (int)(i >> 13);
+    const int mb = chunk / nchunk, ch = chunk % nchunk;
+    const int n = mb * 128 + rr, kk = ch * 64 + k8 * 8 + e;
+    const int l = kk / KL, r = kk % KL;
     const int bb = r / RP, a = r % RP;
     float v = 0.f;
-    if (n < cout && bb < RD && a < RD) v = __ldg(w + (long long)n * (L * RD * RD) + l * RD * RD + a * RD + bb);
+    if (n < cout && kk < K && bb < RD && a < RD) v = __ldg(w + (long long)n * (L * RD * RD) + l * RD * RD + a * RD + bb);
     wp[i] = __float2half_rn(v);
   }
 }
@@ -511,17 +521,18 @@ size_t convc1_pack_bytes(int cout, int levels, int radius) {
   if (!lconv::geometry(radius, &rd, &rp, &kl) || cout < 16 || cout > 256 || cout % 16 || levels < 2 ||
       levels > RCB_MAX_LEVELS)
     return 0;
-  return (size_t)((cout + 127) / 128 * 128) * levels * kl * sizeof(__half);
+  const int nmb = (cout + 127) / 128, nchunk = (levels * kl / 2 + 31) / 32;  // 32-column chunks of a row
+  return (size_t)nmb * nchunk * 8 * 128 * 16;
 }
 
 int launch_convc1_pack(const float* weight, void* wpack, int cout, int levels, int radius, cudaStream_t s) {
   int rd, rp, kl;
   if (!weight || !wpack) return RCB_ERR_INVALID_ARGUMENT;
   if (convc1_pack_bytes(cout, levels, radius) == 0 || !lconv::geometry(radius, &rd, &rp, &kl)) return RCB_ERR_UNSUPPORTED;
-  const int npad = (cout + 127) / 128 * 128;
-  const long long n_el = (long long)npad * levels * kl;
-  lconv::pack_convc1_kernel<<<(int)((n_el + 255) / 256), 256, 0, s>>>(weight, static_cast<__half*>(wpack), cout, npad,
-                                                                     levels, rd, rp, kl);
+  const int nmb = (cout + 127) / 128, nchunk = (levels * kl / 2 + 31) / 32;
+  const long long n_el = (long long)nmb * nchunk * 8 * 128 * 8;
+  lconv::pack_convc1_kernel<<<(int)((n_el + 255) / 256), 256, 0, s>>>(weight, static_cast<__half*>(wpack), cout, nmb,
+                                                                     nchunk, levels, rd, rp, kl);
   return launch_status();
 }
 

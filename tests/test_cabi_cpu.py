@@ -111,7 +111,7 @@ def test_convc1_pack_size_and_argument_checks(lib):
     r = 4 and 64 at r = 3 (window rows padded to even length, levels to a multiple of 16), rows padded to 128."""
     assert lib.rcb_corr_convc1_pack_bytes(256, 4, 4) == 256 * 4 * 96 * 2   # BasicMotionEncoder.convc1 (core/update.py:182)
     assert lib.rcb_corr_convc1_pack_bytes(96, 4, 3) == 128 * 4 * 64 * 2    # SmallMotionEncoder.convc1 (core/update.py:136)
-    assert lib.rcb_corr_convc1_pack_bytes(16, 3, 4) == 128 * 3 * 96 * 2
+    assert lib.rcb_corr_convc1_pack_bytes(16, 3, 4) == 128 * 5 * 64 * 2      # 144 columns -> five 32-column chunks
     for cout, levels, radius in ((24, 4, 4), (272, 4, 4), (0, 4, 4), (256, 1, 4), (256, 5, 4), (256, 4, 2), (256, 4, 5)):
         assert lib.rcb_corr_convc1_pack_bytes(cout, levels, radius) == 0
     buf = (ctypes.c_float * 64)()

@@ -61,7 +61,7 @@ def timeit(fn):
 
 t_fused = timeit(lambda c: blk.lookup_conv(c, packed))
 if os.environ.get("RCB_LCONV_PROF") == "1":
-    prof = torch.zeros(16, dtype=torch.int64, device=dev)
+    prof = torch.zeros(24, dtype=torch.int64, device=dev)
     os.environ["RCB_LCONV_PROF_PTR"] = hex(prof.data_ptr())
     blk.lookup_conv(coords[0], packed)
     torch.cuda.synchronize()
@@ -70,8 +70,8 @@ if os.environ.get("RCB_LCONV_PROF") == "1":
     nm, ne, nt = 148 * 16, 148 * 4, 148
     print("mean cycles per warp: math total %d, wait gather %d, wait s_free %d, resample %d (chunks/warp %.1f) | "
           "mma total %d, wait level_done %d, wait d_free %d, wait weights %d | epilogue total %d, wait acc_full %d, "
-          "weights->tmem %d | math fence+arrive %d, issue %d, prologue %d" % (pr[0] / nm, pr[1] / nm, pr[2] / nm, pr[3] / nm, pr[4] / nm, pr[5] / nt, pr[6] / nt,
-                                pr[7] / nt, pr[8] / nt, pr[9] / ne, pr[10] / ne, pr[12] / ne, pr[13] / nm, pr[14] / nm, pr[15] / nm))
+          "weights->tmem %d | math fence+arrive %d, issue %d, prologue %d (first gathers %d, weights %d)" % (pr[0] / nm, pr[1] / nm, pr[2] / nm, pr[3] / nm, pr[4] / nm, pr[5] / nt, pr[6] / nt,
+                                pr[7] / nt, pr[8] / nt, pr[9] / ne, pr[10] / ne, pr[12] / ne, pr[13] / nm, pr[14] / nm, pr[15] / nm, pr[16] / nm, pr[17] / nm))
 if a.fused_only:
     print(f"debug={os.environ.get('RCB_LCONV_DEBUG', '0')} fused {t_fused:.1f} us")
     sys.exit(0)
