@@ -77,9 +77,10 @@ RCB_DEVINL uint64_t make_desc_interleaved(uint32_t addr, uint32_t lbo, uint32_t 
 
 template <int R, bool PROF>
 __global__ void __launch_bounds__(Cfg<R>::THREADS, 1)
-lookup_conv_kernel(const __grid_constant__ LookupMaps maps, const __grid_constant__ CUtensorMap omap, PyramidDev pyr, const float* __restrict__ coords,
-                   const __half* __restrict__ wpack, const float* __restrict__ bias, float* __restrict__ out, int Q,
-                   int L, int N, int relu, int tiles_q, int ntiles, int tmem_cols, int use_tma_store, int dbg_, unsigned long long* prof_) {
+lookup_conv_kernel(const __grid_constant__ LookupMaps maps, const __grid_constant__ CUtensorMap omap, PyramidDev pyr,
+                   const float* __restrict__ coords, const __half* __restrict__ wpack, const float* __restrict__ bias,
+                   float* __restrict__ out, int Q, int L, int N, int relu, int tiles_q, int ntiles,
+                   unsigned tiles_q_magic, int tmem_cols, int use_tma_store, int dbg_, unsigned long long* prof_) {
   using C = Cfg<R>;
   using G = typename C::G;
   constexpr int RD = C::RD, RP = C::RP, KL = C::KL, ROWS = G::ROWS, NMIN = G::NMIN, NMAX = G::NMAX;
@@ -120,6 +121,9 @@ lookup_conv_kernel(const __grid_constant__ LookupMaps maps, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
   const int tile0 = blockIdx.x, tstep = gridDim.x;
+  // tile -> (batch element, first query) without integer division: tiles_q_magic = 2^32 / tiles_q + 1
+  auto tile_batch = [&](int tile) { return (int)__umulhi((unsigned)tile, tiles_q_magic); };
+  auto tile_q0 = [&](int tile) { return (tile - tile_batch(tile) * tiles_q) * BQ; };
   const int nmb = (N + 127) >> 7;        // 128-channel blocks
   const int KW = (L * KL) >> 1;          // 32-bit weight columns per block
   const uint32_t d_col0 = (uint32_t)(nmb * KW);
@@ -206,7 +210,7 @@ lookup_conv_kernel(const __grid_constant__ LookupMaps maps, const __grid_constan
     const long long clk1 = clock64();
     int i = 0;
     for (int tile = tile0; tile < ntiles; tile += tstep, ++i) {
-      const int bb = tile / tiles_q, qt = (tile % tiles_q) * BQ;
+      const int bb = tile_batch(tile), qt = tile_q0(tile);
       mbar_wait_t(acc_full, (uint32_t)(i & 1), prof ? &w_acc : nullptr);
       tc_fence_after();
       for (int mb = 0; mb < nmb; ++mb) {
@@ -281,7 +285,7 @@ lookup_conv_kernel(const __grid_constant__ LookupMaps maps, const __grid_constan
       bool ok;
     };
     auto load_coords = [&](int tile, float& cx, float& cy) {
-      const int bb = tile / tiles_q, q = (tile % tiles_q) * BQ + m;
+      const int bb = tile_batch(tile), q = tile_q0(tile) + m;
       cx = cy = -1.0e6f;
       if (tile < ntiles && q < Q) {
         cx = __ldg(coords + (long long)(bb * 2 + 0) * Q + q);
@@ -290,7 +294,7 @@ lookup_conv_kernel(const __grid_constant__ LookupMaps maps, const __grid_constan
     };
     auto describe = [&](int tile, int l, float cx, float cy) {
       Pending p;
-      p.ok = (tile % tiles_q) * BQ + m < Q;
+      p.ok = tile_q0(tile) + m < Q;
       p.Hl = l == 0 ? pyr.H[0] : l == 1 ? pyr.H[1] : l == 2 ? pyr.H[2] : pyr.H[3];
       p.Wl = l == 0 ? pyr.W[0] : l == 1 ? pyr.W[1] : l == 2 ? pyr.W[2] : pyr.W[3];
       p.lc = level_coord<R>(cx, cy, l, p.Hl, p.Wl);
@@ -299,7 +303,7 @@ lookup_conv_kernel(const __grid_constant__ LookupMaps maps, const __grid_constan
     auto issue = [&](int tile, int l, int slot, float cx, float cy) {
       const Pending p = describe(tile, l, cx, cy);
       if (sub == 0) {
-        const int bb = tile / tiles_q, q = (tile % tiles_q) * BQ + m;
+        const int bb = tile_batch(tile), q = tile_q0(tile) + m;
         const uint32_t bar = gbar(grp * NS + slot);
         if (p.ok && !(dbg & 2)) {
           const int nx = ((p.lc.xs & 3) + ROWS + 3) >> 2, ny = ((p.lc.ys & 3) + ROWS + 3) >> 2;
@@ -502,14 +506,16 @@ static int launch_r(const LookupPlan& plan, const PyramidDev& pd, const float* c
   const char* pp = getenv("RCB_LCONV_PROF_PTR");  // debug: 16 device uint64 counters supplied by tools/time_lookup_conv.py
   unsigned long long* prof = pp ? reinterpret_cast<unsigned long long*>(strtoull(pp, nullptr, 0)) : nullptr;
   const int tiles_q = (Q + C::BQ - 1) / C::BQ, ntiles = tiles_q * plan.B;
+  const unsigned magic = (unsigned)(0x100000000ull / (unsigned)tiles_q) + 1u;  // exact for tile * tiles_q < 2^32
+  if ((unsigned long long)ntiles * tiles_q >= 0x100000000ull) return RCB_ERR_UNSUPPORTED;
   const int grid = ntiles < kNumSMs ? ntiles : kNumSMs;  // persistent: one CTA per SM walks tiles grid apart
   if (dbg || prof)
     lookup_conv_kernel<R, true><<<grid, C::THREADS, C::SMEM_ALLOC, s>>>(plan.maps, omap, pd, coords, wpack, bias, out, Q,
-                                                                       L, cout, relu, tiles_q, ntiles, tmem_cols,
+                                                                       L, cout, relu, tiles_q, ntiles, magic, tmem_cols,
                                                                        use_tma_store, dbg, prof);
   else
     lookup_conv_kernel<R, false><<<grid, C::THREADS, C::SMEM_ALLOC, s>>>(plan.maps, omap, pd, coords, wpack, bias, out,
-                                                                        Q, L, cout, relu, tiles_q, ntiles, tmem_cols,
+                                                                        Q, L, cout, relu, tiles_q, ntiles, magic, tmem_cols,
                                                                         use_tma_store, 0, nullptr);
   return launch_status();
 }
