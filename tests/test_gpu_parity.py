@@ -572,3 +572,35 @@ def test_lookup_convc1_rejects_what_it_does_not_support(rcb, dev):
     blk = rcb.CorrBlock(t(f1, dev), t(f2, dev), radius=3)
     with pytest.raises(RuntimeError):
         blk.lookup_conv(t(coords, dev), rcb.PackedConvC1(w, None))  # packed for radius 4
+
+
+# ---------------------------------------------------------------------------------------------
+# (10) CUDA graphs: the per-iteration entry points allocate nothing, never synchronise and take the caller's stream,
+# so a GRU loop can be captured once and replayed on new coordinates
+# ---------------------------------------------------------------------------------------------
+def test_lookups_can_be_captured_in_a_cuda_graph(rcb, dev):
+    B, C, H, W, r, L = 2, 64, 24, 40, 4, 4
+    f1, f2, c0 = seeded(77, B, C, H, W)
+    _, _, c1 = seeded(78, B, C, H, W, sigma=6.0)
+    blk = rcb.CorrBlock(t(f1, dev), t(f2, dev), num_levels=L, radius=r)
+    rs = np.random.RandomState(3)
+    wgt = t((rs.standard_normal((96, L * 81, 1, 1)) / 18.0).astype(np.float32), dev)
+    packed = rcb.PackedConvC1(wgt, None, L, r)
+    static_c = t(c0, dev)
+    eager = [(blk(x).clone(), blk.lookup_conv(x, packed).clone()) for x in (t(c0, dev), t(c1, dev))]
+    side = torch.cuda.Stream(dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):  # warm-up on the capture stream (allocator pools, function attributes)
+        blk(static_c), blk.lookup_conv(static_c, packed)
+    torch.cuda.current_stream(dev).wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        a = blk(static_c)          # two dependent-launch lookups back to back, as in the GRU loop
+        b = blk(static_c)
+        c = blk.lookup_conv(static_c, packed)
+    for x, (want_corr, want_conv) in zip((c0, c1), eager):
+        static_c.copy_(t(x, dev))
+        graph.replay()
+        torch.cuda.synchronize(dev)
+        assert torch.equal(a, want_corr) and torch.equal(b, want_corr)
+        assert torch.equal(c, want_conv)
