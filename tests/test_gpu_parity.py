@@ -604,3 +604,50 @@ def test_lookups_can_be_captured_in_a_cuda_graph(rcb, dev):
         torch.cuda.synchronize(dev)
         assert torch.equal(a, want_corr) and torch.equal(b, want_corr)
         assert torch.equal(c, want_conv)
+
+
+# ---------------------------------------------------------------------------------------------
+# (11) several GPUs in one process, as under nn.DataParallel (reference train.py:172, evaluate.py: one Python thread
+# per GPU): blocks on a device that is not the current one, and two devices driven concurrently from two threads
+# ---------------------------------------------------------------------------------------------
+def test_second_device_and_concurrent_threads(rcb, orc):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (run under gpurun --gpus 2)")
+    import threading
+    B, C, H, W, r, L = 2, 64, 23, 39, 4, 4
+    f1, f2, coords = seeded(21, B, C, H, W)
+    want = orc.OracleCorrBlock(f1, f2, num_levels=L, radius=r)(coords, roundtrip=False)
+    rs = np.random.RandomState(9)
+    wgt = (rs.standard_normal((96, L * 81, 1, 1)) / 18.0).astype(np.float32)
+    want_conv = orc.convc1_relu(want, wgt, None)
+    torch.cuda.set_device(0)
+    d1 = torch.device("cuda:1")
+    blk = rcb.CorrBlock(t(f1, d1), t(f2, d1), num_levels=L, radius=r)  # current device is 0
+    assert rel_err(blk(t(coords, d1)).cpu().numpy(), want) < TOL
+    alt = rcb.AlternateCorrBlock(t(f1, d1), t(f2, d1), num_levels=L, radius=r)
+    assert rel_err(alt(t(coords, d1)).cpu().numpy(), want) < TOL
+    got = blk.lookup_conv(t(coords, d1), rcb.PackedConvC1(t(wgt, d1), None, L, r))
+    assert got.device == d1 and rel_err(got.cpu().numpy(), want_conv) < CONVC1_TOL
+    errs = {}
+
+    def worker(idx):
+        try:
+            dev = torch.device("cuda", idx)
+            torch.cuda.set_device(dev)
+            for _ in range(5):
+                b = rcb.CorrBlock(t(f1, dev), t(f2, dev), num_levels=L, radius=r)
+                out = b(t(coords, dev))
+                conv = b.lookup_conv(t(coords, dev), rcb.PackedConvC1(t(wgt, dev), None, L, r))
+                errs[idx] = max(rel_err(out.cpu().numpy(), want), rel_err(conv.cpu().numpy(), want_conv) * TOL / CONVC1_TOL)
+        except Exception as e:  # noqa: BLE001 - reported through the assertion below
+            errs[idx] = e
+
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(2)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    torch.cuda.set_device(0)
+    for i in range(2):
+        assert not isinstance(errs.get(i), Exception), errs.get(i)
+        assert errs[i] < TOL, (i, errs[i])
