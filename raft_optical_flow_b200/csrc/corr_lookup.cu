@@ -37,14 +37,22 @@ namespace rcb {
 // that hands the same output memory to two consecutive calls stays correct.  Any other preceding kernel never
 // triggers, which leaves the ordinary stream order.
 
+// r = 4 only (XROW): a window needs a 4th tile row exactly when it starts in the last pixel row of a tile (py = 3), and
+// then it uses a single pixel row of it.  The TMA box is therefore always 3 tile rows (12 tiles, 768-byte slots instead
+// of 1024) and that one pixel row -- 16 bytes per tile -- is fetched with cp.async into 64 bytes per query.  The
+// smaller slots let 8 CTAs share an SM instead of 6 (36 -> 33 us at cfg2) and the window touches fewer sectors.
 template <int R>
-__global__ void __launch_bounds__(TmaCfg<R>::THREADS, 6)
+__global__ void __launch_bounds__(TmaCfg<R>::THREADS, R == 4 ? 8 : 6)
 lookup_tma_kernel(const __grid_constant__ LookupMaps maps, PyramidDev pyr, const float* __restrict__ coords,
                   float* __restrict__ out, int Q, int L, int dbg) {
   using Cfg = TmaCfg<R>;
-  constexpr int RD = Cfg::RD, ROWS = Cfg::ROWS, NMIN = Cfg::NMIN, NMAX = Cfg::NMAX, SLOT16 = Cfg::SLOT16;
+  constexpr int RD = Cfg::RD, ROWS = Cfg::ROWS, NMIN = Cfg::NMIN, NMAX = Cfg::NMAX;
   constexpr int NBMAX = Cfg::NBMAX, QT = Cfg::QT;
+  constexpr bool XROW = R == 4;
+  constexpr int NYBOX = XROW ? NMAX - 1 : NMAX;  // tile rows a box can have
+  constexpr int SLOT16 = XROW ? (NMAX * NYBOX * 64 + 127) / 128 * 8 : Cfg::SLOT16;
   __shared__ __align__(128) float4 slots[QT * SLOT16];
+  __shared__ __align__(16) float4 xrow[XROW ? QT * 4 : 1];  // [query][tile]: pixel row 0 of the 4th tile row
   __shared__ __align__(8) unsigned long long bars[Cfg::THREADS / 32];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -64,6 +72,7 @@ lookup_tma_kernel(const __grid_constant__ LookupMaps maps, PyramidDev pyr, const
   const LevelCoord lc = level_coord<R>(cx, cy, l, Hl, Wl);
   const int ph = lc.xs & 3, py = lc.ys & 3;
   const int nx = (ph + ROWS + 3) >> 2, ny = (py + ROWS + 3) >> 2;
+  const int nyb = ny < NYBOX ? ny : NYBOX;  // tile rows of the TMA box
 
   // Programmatic dependent launch: consecutive lookups of one GRU loop are independent (each writes its own
   // output), so the next launch may begin its gathers while this one drains; see pdl_wait() below.
@@ -76,12 +85,25 @@ lookup_tma_kernel(const __grid_constant__ LookupMaps maps, PyramidDev pyr, const
   __syncwarp();
   if (sub == 0) {
     if (q_ok && !(dbg & 2)) {
-      mbar_expect_tx(bar, (uint32_t)(nx * ny * 64));
-      tma_load_3d(smem_u32(slots + ql * SLOT16), &maps.m[l * 4 + (ny - NMIN) * 2 + (nx - NMIN)], bar,
+      mbar_expect_tx(bar, (uint32_t)(nx * nyb * 64));
+      tma_load_3d(smem_u32(slots + ql * SLOT16), &maps.m[l * 4 + (nyb - NMIN) * 2 + (nx - NMIN)], bar,
                   (lc.xs >> 2) * 16, lc.ys >> 2, b * Q + q);
     } else {
       mbar_arrive(bar);
     }
+  }
+  if (XROW) {
+    if (q_ok && ny > NYBOX && sub < nx) {  // lane `sub` fetches the row piece of tile `sub`
+      const float* pl = static_cast<const float*>(l == 0 ? pyr.ptr[0] : l == 1 ? pyr.ptr[1] : l == 2 ? pyr.ptr[2] : pyr.ptr[3]);
+      const int txs = l == 0 ? pyr.tiles_x[0] : l == 1 ? pyr.tiles_x[1] : l == 2 ? pyr.tiles_x[2] : pyr.tiles_x[3];
+      const long long ps = l == 0 ? pyr.plane_stride[0] : l == 1 ? pyr.plane_stride[1] : l == 2 ? pyr.plane_stride[2]
+                                                                                              : pyr.plane_stride[3];
+      const int ty = (lc.ys >> 2) + NYBOX, tx = (lc.xs >> 2) + sub;
+      const bool in = ty >= 0 && ty * 4 < Hl && tx >= 0 && tx < txs;  // tiles outside the grid read as zeros
+      const float* src = pl + ((long long)b * Q + q) * ps + (in ? ((long long)(ty * txs + tx) << 4) : 0);
+      cp_async16_zfill(smem_u32(xrow + ql * 4 + sub), src, in ? 16 : 0);
+    }
+    cp_async_commit();
   }
   if (!q_ok) return;
   const float fx = lc.fx, fy = lc.fy, gx = 1.0f - lc.fx, gy = 1.0f - lc.fy;
@@ -91,6 +113,10 @@ lookup_tma_kernel(const __grid_constant__ LookupMaps maps, PyramidDev pyr, const
   const float4* slot = slots + ql * SLOT16;
   const bool ragged_w = (Wl & 3) != 0;
   mbar_wait(bar, 0);
+  if (XROW) {
+    cp_async_wait<0>();
+    __syncwarp();  // the row pieces were fetched by the other lanes of the query
+  }
   if (dbg & 1) return;  // timing experiment: gather only
 
   float hp[RD];
@@ -100,12 +126,14 @@ lookup_tma_kernel(const __grid_constant__ LookupMaps maps, PyramidDev pyr, const
     const int j = b0 + jj;     // window row
     const int ya = py + j;     // row inside the fetched box
     const bool row_ok = lc.ys + j < Hl;  // rows < 0 lie in tile rows the TMA zero-filled
-    const float4* rowp = slot + ((ya >> 2) * nx) * 4 + (ya & 3);
+    const bool ext = XROW && (ya >> 2) >= NYBOX;  // the single pixel row beyond the box
+    const float4* rowp = ext ? xrow + ql * 4 : slot + ((ya >> 2) * nx) * 4 + (ya & 3);
+    const int ks = ext ? 1 : 4;
     float w[4 * NMAX];
 #pragma unroll
     for (int k = 0; k < NMAX; ++k) {
       float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (row_ok && k < nx) u = rowp[k * 4];
+      if (row_ok && k < nx) u = rowp[k * ks];
       w[4 * k + 0] = u.x; w[4 * k + 1] = u.y; w[4 * k + 2] = u.z; w[4 * k + 3] = u.w;
     }
     float v1[ROWS + 2];
