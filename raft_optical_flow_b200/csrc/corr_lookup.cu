@@ -42,7 +42,7 @@ namespace rcb {
 // of 1024) and that one pixel row -- 16 bytes per tile -- is fetched with cp.async into 64 bytes per query.  The
 // smaller slots let 8 CTAs share an SM instead of 6 (36 -> 33 us at cfg2) and the window touches fewer sectors.
 template <int R>
-__global__ void __launch_bounds__(TmaCfg<R>::THREADS, R == 4 ? 8 : 6)
+__global__ void __launch_bounds__(TmaCfg<R>::THREADS, 8)
 lookup_tma_kernel(const __grid_constant__ LookupMaps maps, PyramidDev pyr, const float* __restrict__ coords,
                   float* __restrict__ out, int Q, int L, int dbg) {
   using Cfg = TmaCfg<R>;
@@ -177,7 +177,7 @@ struct TmaCfgH {
 };
 
 template <int R>
-__global__ void __launch_bounds__(TmaCfgH<R>::THREADS, 6)
+__global__ void __launch_bounds__(TmaCfgH<R>::THREADS, 8)
 lookup_tma_f16_kernel(const __grid_constant__ LookupMaps maps, PyramidDev pyr, const float* __restrict__ coords,
                       float* __restrict__ out, int Q, int L) {
   using Cfg = TmaCfgH<R>;
