@@ -14,7 +14,7 @@
 // ~80 % of the measured copy bandwidth for the bytes it really moves).  Four tensor maps per level (the nx x ny
 // combinations) live in a host-side plan that is encoded once per pyramid, not per call.
 //   CTA   = 32 consecutive queries of ONE level, 128 threads, a warp owns 8 queries end to end: lane 4i issues
-//           the box of query i on the warp's own mbarrier, the warp waits, then does the math; six CTAs per SM
+//           the box of query i on the warp's own mbarrier, the warp waits, then does the math; eight CTAs per SM
 //           keep ~100 KB of gathers in flight.
 //   math  = the 4 lanes of a query split the (2r+1) y offsets; a lane reads its 3-4 window rows as whole tile
 //           rows (LDS.128), aligns them to the window's 4-byte phase with two select stages, applies the separable
