@@ -226,6 +226,11 @@ lookup_tma_f16_kernel(const __grid_constant__ LookupMaps maps, PyramidDev pyr, c
   const long long sa = (long long)RD * Q;
   const uint4* slot = slots + ql * SLOT16;
   const bool ragged_w = (Wl & 7) != 0;
+  constexpr int NP = (ROWS / 2 + 3) / 2;                 // 8-byte pairs that cover ROWS / 2 + 2 words
+  const int pair_step = ph >> 2;                         // whole pairs the window starts into the row
+  const int off_even = pair_step * 8, off_odd = pair_step * 56;
+  const bool word_step = (ph >> 1) & 1;
+  const uint32_t half_sel = (ph & 1) ? 0x5432u : 0x3210u;
   mbar_wait(bar, 0);
 
   float hp[RD];
@@ -235,29 +240,27 @@ lookup_tma_f16_kernel(const __grid_constant__ LookupMaps maps, PyramidDev pyr, c
     const int j = b0 + jj;     // window row
     const int ya = py + j;     // row inside the fetched box
     const bool row_ok = lc.ys + j < Hl;  // rows < 0 lie in tile rows the TMA zero-filled
-    const uint4* rowp = slot + ((ya >> 2) * nx) * 4 + (ya & 3);
-    float w[8 * NMAXX];
+    // The ROWS taps start ph halfs (0..7) into the row.  Whole 8-byte pairs of that offset are folded into the load
+    // addresses (a tile row is 16 bytes, the next tile 64 bytes further), the remaining 4-byte step is one select
+    // stage on packed words and the odd half is a byte permute; only the ROWS taps are then widened to fp32.
+    const unsigned char* rb = reinterpret_cast<const unsigned char*>(slot + ((ya >> 2) * nx) * 4 + (ya & 3));
+    uint32_t x[2 * NP];
 #pragma unroll
-    for (int k = 0; k < NMAXX; ++k) {
-      uint4 u = make_uint4(0u, 0u, 0u, 0u);
-      if (row_ok && k < nx) u = rowp[k * 4];
-      const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
-      const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
-      const float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(&u.z));
-      const float2 f3 = __half22float2(*reinterpret_cast<const __half2*>(&u.w));
-      w[8 * k + 0] = f0.x; w[8 * k + 1] = f0.y; w[8 * k + 2] = f1.x; w[8 * k + 3] = f1.y;
-      w[8 * k + 4] = f2.x; w[8 * k + 5] = f2.y; w[8 * k + 6] = f3.x; w[8 * k + 7] = f3.y;
+    for (int k = 0; k < NP; ++k) {
+      const uint2 pr = *reinterpret_cast<const uint2*>(rb + (k >> 1) * 64 + ((k & 1) ? 8 + off_odd : off_even));
+      x[2 * k] = pr.x;
+      x[2 * k + 1] = pr.y;
     }
-    // t[i] = w[ph + i], ph = 0..7: three select stages
-    float v1[ROWS + 6];
-#pragma unroll
-    for (int i = 0; i < ROWS + 6; ++i) v1[i] = (ph & 1) ? w[i + 1] : w[i];
-    float v2[ROWS + 4];
-#pragma unroll
-    for (int i = 0; i < ROWS + 4; ++i) v2[i] = (ph & 2) ? v1[i + 2] : v1[i];
     float t[ROWS];
 #pragma unroll
-    for (int i = 0; i < ROWS; ++i) t[i] = (ph & 4) ? v2[i + 4] : v2[i];
+    for (int i = 0; i < ROWS / 2; ++i) {
+      const uint32_t y0 = word_step ? x[i + 1] : x[i], y1 = word_step ? x[i + 2] : x[i + 1];
+      uint32_t z = __byte_perm(y0, y1, half_sel);
+      if (!row_ok) z = 0u;
+      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&z));
+      t[2 * i] = f.x;
+      t[2 * i + 1] = f.y;
+    }
     if (ragged_w) {
 #pragma unroll
       for (int i = 0; i < ROWS; ++i)
