@@ -11,6 +11,11 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--config", default="cfg2")
 ap.add_argument("--mode", default="bf16x3")
 ap.add_argument("--reps", type=int, default=20)
+ap.add_argument("--between", default="none", choices=["none", "lookups", "fill", "sleep"],
+                help="what runs between the timed builds: nothing (tight loop), the step's lookups, a 512 MB fill, "
+                     "or ~1 ms of idle")
+ap.add_argument("--python", action="store_true", help="with --between lookups: go through CorrBlock(...) and blk(coords) "
+                "like bench.py instead of the raw C calls on preallocated buffers")
 a = ap.parse_args()
 B, C, H, W, r, L, iters, _ = CONFIGS[a.config]
 dev = torch.device("cuda:0")
@@ -36,6 +41,37 @@ for _ in range(a.reps):
 e1.record()
 t1 = time.perf_counter()
 torch.cuda.synchronize()
+if a.between != "none":
+    # each build timed on its own, with something else on the stream in between (what the bench step looks like)
+    from raft_optical_flow_b200 import CorrBlock
+    plan = _cabi.LookupPlan(pyr.ptrs, B, H, W, L, r, 0)
+    ys, xs = torch.meshgrid(torch.arange(H), torch.arange(W), indexing="ij")
+    coords = (torch.stack([xs, ys]).float()[None] + 4.0 * torch.randn(B, 2, H, W, generator=g)).to(dev).contiguous()
+    outs = [torch.empty((B, L * (2 * r + 1) ** 2, H, W), device=dev) for _ in range(2)]
+    junk = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.reps)]
+    blk = None
+    for k in range(a.reps if not a.python else 0):
+        if a.between == "lookups":
+            for i in range(iters):
+                _cabi.check(lib.rcb_corr_lookup_planned(plan.ptr, coords.data_ptr(), outs[i & 1].data_ptr(), s), "lookup")
+        elif a.between == "fill":
+            junk.fill_(k & 255)
+        else:
+            torch.cuda._sleep(2_000_000)
+        evs[k][0].record()
+        call()
+        evs[k][1].record()
+    cs = [coords.clone() for _ in range(iters)]
+    for k in range(a.reps if a.python else 0):
+        evs[k][0].record()
+        blk = CorrBlock(f1, f2, num_levels=L, radius=r, mode=a.mode)
+        evs[k][1].record()
+        for i in range(iters):
+            out = blk(cs[i])
+    torch.cuda.synchronize()
+    ts = sorted(x.elapsed_time(y) * 1e3 for x, y in evs[2:])
+    print(f"{a.config} {a.mode} between={a.between}: build median {ts[len(ts) // 2]:.1f} us, min {ts[0]:.1f}, max {ts[-1]:.1f}")
 if os.environ.get("RCB_TC_PROF") == "1":
     prof = torch.zeros(16 * 148, dtype=torch.int64, device=dev)
     os.environ["RCB_TC_PROF_PTR"] = hex(prof.data_ptr())
