@@ -651,3 +651,29 @@ def test_second_device_and_concurrent_threads(rcb, orc):
     for i in range(2):
         assert not isinstance(errs.get(i), Exception), errs.get(i)
         assert errs[i] < TOL, (i, errs[i])
+
+
+# ---------------------------------------------------------------------------------------------
+# (12) seeded sweep over small odd geometries: windows that start in every phase of the 4x4 tiles, planes whose last
+# tile row / column is ragged, pooled levels down to 1-2 pixels, coordinates far outside on every side
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("seed", range(12))
+def test_lookup_sweep_of_small_geometries_vs_oracle(rcb, dev, orc, seed):
+    rs = np.random.RandomState(1000 + seed)
+    B, C = int(rs.randint(1, 3)), int(rs.choice([8, 20, 32]))
+    H, W = int(rs.randint(8, 41)), int(rs.randint(8, 41))
+    r = int(rs.choice([3, 4, 4, 4]))
+    L = 4 if min(H, W) >= 16 else 3
+    f1 = rs.standard_normal((B, C, H, W)).astype(np.float32)
+    f2 = rs.standard_normal((B, C, H, W)).astype(np.float32)
+    ys, xs = np.meshgrid(np.arange(H), np.arange(W), indexing="ij")
+    coords = (np.stack([xs, ys])[None] + 5.0 * rs.standard_normal((B, 2, H, W))).astype(np.float32)
+    coords[:, 0, 0, :] = np.linspace(-12.0, W + 11.0, W, dtype=np.float32)  # sweeps across the left and right borders
+    coords[:, 1, :, 0] = np.linspace(-12.0, H + 11.0, H, dtype=np.float32)  # ... and the top and bottom ones
+    coords[:, :, -1, -1] = np.float32(3.0) + np.float32(1.0) / np.float32(3.0)  # window starting in tile row phase 3
+    want = orc.OracleCorrBlock(f1, f2, num_levels=L, radius=r)(coords, roundtrip=False)
+    for pdt, tol in (("f32", TOL), ("f16", 2e-3)):
+        blk = rcb.CorrBlock(t(f1, dev), t(f2, dev), num_levels=L, radius=r, pyramid_dtype=pdt)
+        got = blk(t(coords, dev)).cpu().numpy()
+        assert np.isfinite(got).all()
+        assert rel_err(got, want) < tol, (seed, pdt, B, C, H, W, r, L)
