@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define RCB_ABI_VERSION 6
+#define RCB_ABI_VERSION 7
 #define RCB_MAX_LEVELS 4 /* core/raft.py:46-53 fixes corr_levels = 4 */
 #define RCB_MAX_RADIUS 4 /* core/raft.py:47,53: radius 3 (small) / 4 (full) */
 
@@ -55,6 +55,11 @@ enum rcb_build_mode {
   RCB_BUILD_BF16X3 = 1,    /* tcgen05: hi/lo bf16 split, 3 products, fp32 accumulate in TMEM;
                               error ~2e-6 of max-abs -- the default fp32-parity mode */
   RCB_BUILD_BF16 = 2,      /* tcgen05: single bf16 pass, fp32 accumulate; ~1e-3 of max-abs */
+  RCB_BUILD_F16F8 = 3,     /* tcgen05: hi = fp16(x) on kind::f16 (one pass) + the two cross terms hi*lo, lo*hi in
+                              8-bit e4m3 on kind::f8f6f4 (twice the rate), fp32 accumulate in TMEM: two
+                              pass-equivalents instead of three; error ~1e-5 of max-abs -- the default
+                              fp32-parity mode.  Feature magnitudes must stay below the fp16 range (65504);
+                              use RCB_BUILD_BF16X3 for unbounded inputs */
 };
 
 /* Memory layout of the pyramid the build writes and the lookup reads.
@@ -91,7 +96,7 @@ RCB_API int rcb_pyramid_layout_query(int B, int H, int W, int levels, int dtype,
  *   fmap1, fmap2 : [B, C, H, W] fp32 (core/raft.py:181-182)
  *   pyr[l]       : level-l buffer laid out as rcb_pyramid_layout says, l < levels
  *   level l > 0 equals the 2x2 floor-mode mean of level l-1.
- * `workspace` holds the packed bf16 operands of the tensor-core modes (unused for FP32_SIMT). */
+ * `workspace` holds the packed operands of the tensor-core modes (unused for FP32_SIMT), 128-byte aligned. */
 RCB_API size_t rcb_corr_build_workspace_bytes(int B, int C, int H, int W, int mode);
 RCB_API int rcb_corr_build(const float* fmap1, const float* fmap2, void* const* pyr, int B, int C, int H, int W,
                    int levels, int mode, int pyr_dtype, void* workspace, size_t workspace_bytes,

@@ -8,15 +8,17 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libraftcorr_b200.so")
+if os.environ.get("RCB_USE_DEBUG_LIB") == "1":  # timing / profiling hooks (tools/time_*.py); see build.py --debug
+    LIB_PATH = os.path.join(HERE, "libraftcorr_b200_debug.so")
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 MAX_LEVELS = 4
 MAX_RADIUS = 4
 
 # enum rcb_dtype / rcb_build_mode
 F32, F16 = 0, 1
-BUILD_FP32_SIMT, BUILD_BF16X3, BUILD_BF16 = 0, 1, 2
-BUILD_MODES = {"fp32": BUILD_FP32_SIMT, "bf16x3": BUILD_BF16X3, "bf16": BUILD_BF16}
+BUILD_FP32_SIMT, BUILD_BF16X3, BUILD_BF16, BUILD_F16F8 = 0, 1, 2, 3
+BUILD_MODES = {"fp32": BUILD_FP32_SIMT, "bf16x3": BUILD_BF16X3, "bf16": BUILD_BF16, "f16f8": BUILD_F16F8}
 
 _vp = ctypes.c_void_p
 _i = ctypes.c_int

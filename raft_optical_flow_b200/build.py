@@ -1,6 +1,11 @@
 """Compiles raft_optical_flow_b200/csrc/*.cu into libraftcorr_b200.so (in-tree, next to this file).
 
-    python -m raft_optical_flow_b200.build [--force]
+    python -m raft_optical_flow_b200.build [--force] [--debug]
+
+--debug additionally compiles libraftcorr_b200_debug.so with -DRCB_DEBUG: the same kernels plus the timing /
+profiling hooks that tools/time_*.py drive through environment variables (RCB_TC_DEBUG_SKIP, RCB_TC_PROF_PTR,
+RCB_LOOKUP_DEBUG, RCB_LCONV_* ...).  The release library ignores the environment entirely; the Python binding loads
+the debug library only when RCB_USE_DEBUG_LIB=1 is set.
 
 sm_100a only (B200): nvcc cross-compiles without a GPU.  The library exports the C ABI declared in
 include/raft_corr_b200.h and nothing else; it links the CUDA runtime statically and resolves the one
@@ -14,6 +19,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libraftcorr_b200.so")
+DEBUG_LIB = os.path.join(HERE, "libraftcorr_b200_debug.so")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-shared",
@@ -25,26 +31,30 @@ def sources():
     return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
 
 
-def needs_build():
-    if not os.path.exists(LIB):
+def needs_build(lib=LIB):
+    if not os.path.exists(lib):
         return True
     deps = sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + \
         glob.glob(os.path.join(HERE, "..", "include", "*.h"))
-    return any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in deps)
+    return any(os.path.getmtime(d) > os.path.getmtime(lib) for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
-        return LIB
+def build(force=False, verbose=False, debug=False):
+    lib = DEBUG_LIB if debug else LIB
+    if not force and not needs_build(lib):
+        return lib
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + sources()
+    cmd = [nvcc] + NVCC_FLAGS + (["-DRCB_DEBUG"] if debug else []) + (["-Xptxas", "-v"] if verbose else []) + \
+        ["-o", lib] + sources()
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
     if verbose:
         print(res.stderr)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--debug" in sys.argv:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, debug=True))

@@ -7,8 +7,10 @@ device memory, streams and autograd plumbing only.  There is no CPU path: tensor
 device (same error text as the reference extension, alt_cuda_corr/correlation.cpp:19).
 
 Build modes of the all-pairs volume (``mode=`` / env ``RAFT_CORR_MODE``):
-  "bf16x3" (default)  tcgen05 tensor cores, hi/lo bf16 split, fp32 accumulate  -> fp32-parity (<=1e-4 rel)
-  "fp32"              fp32 FMA pipe, the reference's exact arithmetic class
+  "f16f8" (default)   tcgen05 tensor cores: fp16 hi x hi pass + the two cross terms in 8-bit e4m3 (kind::f8f6f4),
+                      fp32 accumulate -> fp32-parity (~1e-5 of max-abs, bound 1e-4); |features| < 65504
+  "bf16x3"            tcgen05 tensor cores, hi/lo bf16 split, three passes, fp32 accumulate -> fp32-parity (~5e-6)
+  "fp32"              fp32 FMA pipe, the reference's exact arithmetic class (also used for C > 256)
   "bf16"              single-pass bf16 operands (fast mode, ~1e-3 rel)
 """
 import math
@@ -21,7 +23,7 @@ from . import _cabi
 
 __all__ = ["CorrBlock", "AlternateCorrBlock", "PackedConvC1"]
 
-DEFAULT_MODE = os.environ.get("RAFT_CORR_MODE", "bf16x3")
+DEFAULT_MODE = os.environ.get("RAFT_CORR_MODE", "f16f8")
 
 
 def _stream(t):
@@ -72,6 +74,8 @@ class _Pyramid:
 def _build(f1, f2, levels, mode, pyr):
     B, C, H, W = f1.shape
     lib = _cabi.lib()
+    if C > 256 and pyr.dtype == _cabi.F32:
+        mode = _cabi.BUILD_FP32_SIMT  # the tensor-core kernels keep the query operand in tensor memory: C <= 256
     ws_bytes = lib.rcb_corr_build_workspace_bytes(B, C, H, W, mode)
     ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=f1.device)
     with torch.cuda.device(f1.device):

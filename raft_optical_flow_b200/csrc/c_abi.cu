@@ -47,7 +47,8 @@ int rcb_corr_build(const float* fmap1, const float* fmap2, void* const* pyr, int
   switch (mode) {
     case RCB_BUILD_FP32_SIMT: return launch_build_simt(fmap1, fmap2, pyr, lay, B, C, H, W, s);
     case RCB_BUILD_BF16X3:
-    case RCB_BUILD_BF16: return launch_build_tc(fmap1, fmap2, pyr, lay, B, C, H, W, mode, workspace, workspace_bytes, s);
+    case RCB_BUILD_BF16:
+    case RCB_BUILD_F16F8: return launch_build_tc(fmap1, fmap2, pyr, lay, B, C, H, W, mode, workspace, workspace_bytes, s);
     default: return RCB_ERR_UNSUPPORTED;
   }
 }

@@ -319,9 +319,9 @@ static cudaLaunchConfig_t pdl_config(dim3 grid, int threads, cudaStream_t s) {
   cfg.stream = s;
   return cfg;
 }
-// RCB_LOOKUP_PDL=0 launches with ordinary stream serialization (A/B timing)
+// RCB_LOOKUP_PDL=0 (RCB_DEBUG builds only) launches with ordinary stream serialization (A/B timing)
 static int pdl_attribute(cudaLaunchAttribute* attr) {
-  static const bool on = [] { const char* e = getenv("RCB_LOOKUP_PDL"); return !(e && e[0] == '0'); }();
+  static const bool on = debug_env_int("RCB_LOOKUP_PDL", 1) != 0;
   if (!on) return 0;
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
@@ -334,7 +334,7 @@ static int launch_lookup_tma_r(const LookupPlan& plan, const PyramidDev& pd, con
   using Cfg = TmaCfg<R>;
   const int Q = plan.H * plan.W;
   dim3 grid((Q + Cfg::QT - 1) / Cfg::QT, plan.lay.levels, plan.B);
-  static const int dbg = [] { const char* e = getenv("RCB_LOOKUP_DEBUG"); return e ? atoi(e) : 0; }();
+  static const int dbg = debug_env_int("RCB_LOOKUP_DEBUG", 0);  // RCB_DEBUG builds only
   cudaLaunchConfig_t cfg = pdl_config(grid, Cfg::THREADS, s);
   cudaLaunchAttribute attr[1];
   cfg.numAttrs = pdl_attribute(attr);

@@ -492,7 +492,7 @@ static int launch_r(const LookupPlan& plan, const PyramidDev& pd, const float* c
   int tmem_cols = 32;
   while (tmem_cols < need) tmem_cols *= 2;
   if (tmem_cols > 512) return RCB_ERR_UNSUPPORTED;
-  static const int dbg = getenv("RCB_LCONV_DEBUG") ? atoi(getenv("RCB_LCONV_DEBUG")) : 0;  // timing experiments
+  static const int dbg = debug_env_int("RCB_LCONV_DEBUG", 0);  // timing experiments (RCB_DEBUG builds only)
   // output as a [B][N][Q] tensor for the epilogue's TMA stores (needs 16-byte row pitch)
   CUtensorMap omap;
   int use_tma_store = (Q % 4 == 0) && encode_fn() != nullptr;
@@ -503,8 +503,8 @@ static int launch_r(const LookupPlan& plan, const PyramidDev& pd, const float* c
     if (!encode(&omap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, out, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B)) use_tma_store = 0;
   }
   if (!use_tma_store) memset(&omap, 0, sizeof(omap));
-  const char* pp = getenv("RCB_LCONV_PROF_PTR");  // debug: 16 device uint64 counters supplied by tools/time_lookup_conv.py
-  unsigned long long* prof = pp ? reinterpret_cast<unsigned long long*>(strtoull(pp, nullptr, 0)) : nullptr;
+  // RCB_DEBUG builds only: device uint64 counters supplied by tools/time_lookup_conv.py
+  unsigned long long* prof = debug_env_ptr("RCB_LCONV_PROF_PTR");
   const int tiles_q = (Q + C::BQ - 1) / C::BQ, ntiles = tiles_q * plan.B;
   const unsigned magic = (unsigned)(0x100000000ull / (unsigned)tiles_q) + 1u;  // exact for tile * tiles_q < 2^32
   if ((unsigned long long)ntiles * tiles_q >= 0x100000000ull) return RCB_ERR_UNSUPPORTED;

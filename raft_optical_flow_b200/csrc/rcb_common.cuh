@@ -14,6 +14,25 @@ namespace rcb {
 
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
 
+// Debug / profiling hooks (timing experiments of tools/time_*.py: skip phases of a kernel, cycle counters written
+// through a raw device pointer, alternative tunings).  They exist ONLY in a library compiled with -DRCB_DEBUG
+// (`python -m raft_optical_flow_b200.build --debug` -> libraftcorr_b200_debug.so); the release library never
+// reads the environment, so a stray variable in a job's environment cannot change results or touch memory.
+#ifdef RCB_DEBUG
+#include <cstdlib>
+inline int debug_env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+inline unsigned long long* debug_env_ptr(const char* name) {
+  const char* e = getenv(name);
+  return e ? reinterpret_cast<unsigned long long*>(strtoull(e, nullptr, 0)) : nullptr;
+}
+#else
+inline int debug_env_int(const char*, int dflt) { return dflt; }
+inline unsigned long long* debug_env_ptr(const char*) { return nullptr; }
+#endif
+
 inline int launch_status() {
   cudaError_t e = cudaPeekAtLastError();
   return e == cudaSuccess ? RCB_OK : (int)e;

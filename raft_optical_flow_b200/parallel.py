@@ -47,18 +47,87 @@ def max_over_ranks(values, device=None):
     return t.tolist()
 
 
+_binding = {"desc": "not bound"}
+
+
+def _gpu_cpu_affinity(local):
+    """CPUs the driver reports as local to GPU `local` (NVML), or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            uuid = str(torch.cuda.get_device_properties(local).uuid)
+            handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
+        except Exception:  # noqa: BLE001 -- older torch / masked devices: fall back to the index
+            handle = pynvml.nvmlDeviceGetHandleByIndex(local)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(handle, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+        return cpus or None
+    except Exception:  # noqa: BLE001
+        return None
+
+
+def bind_to_gpu_cpus(local, local_world=None):
+    """Pins the calling process to its own share of the host CPUs next to GPU `local` (one process per GPU): the CPUs
+    NVML reports as local to the GPU (its NUMA node), intersected with what the process may use, and split evenly
+    between the ranks of the node so that the launch threads and the pinned staging buffers of different ranks do not
+    migrate onto each other.  Call before allocating pinned memory.  Returns the CPU set (also on hosts without NVML,
+    where the allowed set is split instead)."""
+    if local_world is None:
+        local_world = int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")))
+    allowed = sorted(os.sched_getaffinity(0))
+    near = _gpu_cpu_affinity(local)
+    pool = [c for c in allowed if near is None or c in near] or allowed
+    if local_world > 1 and len(pool) >= local_world:
+        # ranks that share a pool (same NUMA node) take disjoint slices of it
+        per = len(pool) // local_world
+        mine = pool[(local % local_world) * per:(local % local_world + 1) * per]
+    else:
+        mine = pool
+    try:
+        os.sched_setaffinity(0, mine)
+        torch.set_num_threads(max(1, min(len(mine), torch.get_num_threads())))
+        _binding["desc"] = (f"{len(mine)} of {len(allowed)} host CPUs ({mine[0]}-{mine[-1]}), "
+                            f"{'NVML affinity of the GPU' if near else 'even split of the allowed set'}")
+    except OSError as e:
+        _binding["desc"] = f"not bound ({e})"
+    return mine
+
+
+def binding_description():
+    return _binding["desc"]
+
+
+def _dense_grads(params):
+    """Gradient tensors of every parameter that requires grad, in the given (rank-independent) order; a parameter
+    that received no gradient on this rank contributes zeros so that all ranks reduce identical layouts."""
+    out = []
+    for p in params:
+        if not p.requires_grad:
+            continue
+        if p.grad is None:
+            p.grad = torch.zeros_like(p)
+        out.append(p.grad)
+    return out
+
+
 def allreduce_grads(params, bucket_bytes=32 << 20, average=True):
-    """Sums (or averages) the .grad of `params` over all ranks in flat buckets of ~bucket_bytes.
-    RAFT-full has 5 257 536 fp32 parameters = 21 MB: one bucket; on NVSwitch the cost is launch
-    latency, so buckets are sized for few launches rather than for link count.  Returns the launch count."""
-    grads = [p.grad for p in params if p.grad is not None]
-    if not grads or not dist.is_initialized() or dist.get_world_size() == 1:
+    """Sums (or averages) the .grad of `params` over all ranks in flat buckets of ~bucket_bytes, after backward has
+    finished (see GradBucketReducer for the overlapped form).  Buckets cover EVERY parameter that requires grad, in
+    the given order, with zeros standing in for a missing .grad, and never mix dtypes -- so the layout is identical
+    on all ranks whatever each rank's graph touched.  RAFT-full has 5 257 536 fp32 parameters = 21 MB:
+    one bucket.  Returns the launch count."""
+    params = list(params)
+    if not dist.is_initialized() or dist.get_world_size() == 1:
         return 0
+    grads = _dense_grads(params)
     world = dist.get_world_size()
-    state = {"launches": 0, "bucket": [], "size": 0}
+    launches = 0
+    bucket, size = [], 0
 
     def flush():
-        bucket = state["bucket"]
+        nonlocal bucket, size, launches
         if not bucket:
             return
         flat = torch.cat([g.reshape(-1) for g in bucket])
@@ -69,13 +138,104 @@ def allreduce_grads(params, bucket_bytes=32 << 20, average=True):
         for g in bucket:
             g.copy_(flat[off:off + g.numel()].view_as(g))
             off += g.numel()
-        state["launches"] += 1
-        state["bucket"], state["size"] = [], 0
+        launches += 1
+        bucket, size = [], 0
 
     for g in grads:
-        state["bucket"].append(g)
-        state["size"] += g.numel() * g.element_size()
-        if state["size"] >= bucket_bytes:
+        if bucket and bucket[0].dtype != g.dtype:
+            flush()
+        bucket.append(g)
+        size += g.numel() * g.element_size()
+        if size >= bucket_bytes:
             flush()
     flush()
-    return state["launches"]
+    return launches
+
+
+class GradBucketReducer:
+    """Gradient all-reduce overlapped with backward: the one-process-per-GPU replacement of what nn.DataParallel does
+    at the end of backward (reference train.py:172,212).
+
+    Parameters are grouped into fixed buckets of ~bucket_bytes in REVERSE registration order (the order backward
+    produces gradients in), one dtype per bucket, identical on every rank.  A post-accumulate-grad hook on every
+    parameter counts the bucket down; when a bucket is complete its gradients are flattened and an asynchronous
+    all_reduce is launched at once (NCCL: on the communicator's own stream, so it runs under the rest of backward;
+    gloo in the CPU tests), while autograd keeps producing the earlier layers' gradients.  ``finish()`` -- called
+    after ``loss.backward()`` -- flushes buckets some of whose parameters got no gradient this step (zeros stand in),
+    waits for the handles and scatters the averaged values back into ``.grad``.
+    """
+
+    def __init__(self, params, bucket_bytes=4 << 20, average=True):
+        self.params = [p for p in params if p.requires_grad]
+        self.average = average
+        self.enabled = dist.is_initialized() and dist.get_world_size() > 1
+        self.buckets = []          # lists of parameters
+        cur, size = [], 0
+        for p in reversed(self.params):
+            if cur and (cur[0].dtype != p.dtype or size >= bucket_bytes):
+                self.buckets.append(cur)
+                cur, size = [], 0
+            cur.append(p)
+            size += p.numel() * p.element_size()
+        if cur:
+            self.buckets.append(cur)
+        self._bucket_of = {id(p): i for i, b in enumerate(self.buckets) for p in b}
+        self._hooks = []
+        if self.enabled:
+            for p in self.params:
+                self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad))
+        self.launch_order = []     # bucket indices in the order their all-reduce was launched (last step)
+        self._reset()
+
+    def _reset(self):
+        self._pending = [len(b) for b in self.buckets]
+        self._ready = [set() for _ in self.buckets]
+        self._inflight = {}
+
+    def _on_grad(self, p):
+        i = self._bucket_of[id(p)]
+        if id(p) in self._ready[i]:
+            return  # a second accumulation into the same .grad within one step (not expected in RAFT)
+        self._ready[i].add(id(p))
+        self._pending[i] -= 1
+        if self._pending[i] == 0:
+            self._launch(i)
+
+    def _launch(self, i):
+        grads = []
+        for p in self.buckets[i]:
+            if p.grad is None:
+                p.grad = torch.zeros_like(p)
+            grads.append(p.grad)
+        flat = torch.cat([g.reshape(-1) for g in grads])
+        handle = dist.all_reduce(flat, op=dist.ReduceOp.SUM, async_op=True)
+        self._inflight[i] = (flat, handle, grads)
+        self.launch_order.append(i)
+
+    def finish(self):
+        """Call after backward.  Returns the number of all-reduce launches of this step."""
+        if not self.enabled:
+            return 0
+        for i in range(len(self.buckets)):
+            if i not in self._inflight:  # some parameter of the bucket received no gradient on this rank
+                self._launch(i)
+        world = dist.get_world_size()
+        for i, (flat, handle, grads) in self._inflight.items():
+            handle.wait()
+            if self.average:
+                flat.div_(world)
+            off = 0
+            for g in grads:
+                g.copy_(flat[off:off + g.numel()].view_as(g))
+                off += g.numel()
+        n = len(self._inflight)
+        self._reset()
+        return n
+
+    def begin_step(self):
+        self.launch_order = []
+
+    def remove(self):
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []

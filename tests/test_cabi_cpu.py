@@ -34,7 +34,7 @@ def test_library_exports_every_declared_symbol(lib):
 
 
 def test_status_strings(lib):
-    assert lib.rcb_abi_version() == 6
+    assert lib.rcb_abi_version() == 7
     assert lib.rcb_status_string(0) == b"ok"
     assert b"invalid" in lib.rcb_status_string(-1)
     assert b"unsupported" in lib.rcb_status_string(-2)

@@ -2,7 +2,13 @@
 iterations"): the UNMODIFIED reference RAFT (core/raft.py, RAFT-small with the shipped raft-small.pth, demo
 frames 0016/0017 padded to 440x1024) is run on the GPU once with its own CorrBlock (torch ops) and once with
 this package's blocks patched in at the names core/raft.py:187,189 looks up.  The reference files travel as
-oracle/_ref/reference_raft.tar (built by oracle/stage_reference.py where the reference checkout exists)."""
+oracle/_ref/reference_raft.tar (built by oracle/stage_reference.py where the reference checkout exists).
+
+Both arms run with TF32 switched OFF for cuDNN convolutions and matmuls (torch enables TF32 convolutions by
+default), so that the encoders and the update block compute the same fp32 numbers in both arms and the measured
+end-point-error delta isolates the correlation path.  Bounds: fp32-parity modes (fp32, bf16x3, f16f8 operands with an
+fp32 pyramid, the on-the-fly blocks, the fused upsampling) MAX per-pixel delta <= 0.01 px; reduced-precision fast modes
+(single-pass bf16 operands, fp16-stored pyramid, fp16 fused convc1) MEAN delta <= 0.01 px, max printed."""
 import argparse
 import os
 import sys
@@ -16,6 +22,19 @@ pytestmark = pytest.mark.gpu
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 TAR = os.path.join(ROOT, "oracle", "_ref", "reference_raft.tar")
+EPE_BOUND = 0.01  # px, BASELINE.json
+PARITY = ("fp32", "bf16x3", "f16f8")  # build modes that claim fp32 parity (with an fp32 pyramid)
+
+
+@pytest.fixture(scope="module", autouse=True)
+def no_tf32():
+    """fp32 everywhere outside the correlation path, in BOTH arms."""
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.benchmark = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark = old
 
 
 @pytest.fixture(scope="module")
@@ -79,15 +98,20 @@ def test_corrblock_dropin_flow_matches_reference(ref, iters):
     model, i1, i2 = _load(d, raft_mod, InputPadder, alternate=False)
     want = _flow(model, i1, i2, iters)
     assert want.abs().max().item() > 5.0  # a real flow field (reference CPU run: max-abs 10.6)
+    floor = _epe(_flow(model, i1, i2, iters), want)  # reference vs reference: run-to-run noise of everything else
+    print(f"iters={iters} reference vs reference: EPE delta mean {floor[0]:.2e} px, max {floor[1]:.2e} px")
     orig = raft_mod.CorrBlock
     try:
-        for mode, pdt, bound in (("bf16x3", "f32", 0.01), ("fp32", "f32", 0.01), ("bf16", "f32", 0.05),
-                                 ("bf16x3", "f16", 0.01), ("bf16", "f16", 0.05)):
+        for mode, pdt in (("bf16x3", "f32"), ("f16f8", "f32"), ("fp32", "f32"), ("bf16", "f32"), ("bf16x3", "f16"),
+                          ("bf16", "f16")):
             raft_mod.CorrBlock = lambda f1, f2, radius=4, _m=mode, _p=pdt: rcb.CorrBlock(f1, f2, radius=radius, mode=_m,
                                                                                            pyramid_dtype=_p)
             mean, mx = _epe(_flow(model, i1, i2, iters), want)
             print(f"iters={iters} mode={mode} pyramid={pdt}: EPE delta mean {mean:.2e} px, max {mx:.2e} px")
-            assert mean <= bound and (mode == "bf16" or mx <= 0.05), (mode, pdt, mean, mx)
+            if mode in PARITY and pdt == "f32":
+                assert mx <= EPE_BOUND, (mode, pdt, mean, mx)
+            else:
+                assert mean <= EPE_BOUND, (mode, pdt, mean, mx)
     finally:
         raft_mod.CorrBlock = orig
 
@@ -105,11 +129,11 @@ def test_patch_raft_with_fused_upsampling_matches_reference(ref):
     try:
         mean, mx = _epe(_flow(model, i1, i2, 12), want)
         print(f"patch_raft: EPE delta mean {mean:.2e} px, max {mx:.2e} px")
-        assert mean <= 0.01 and mx <= 0.05
+        assert mx <= EPE_BOUND
         with torch.no_grad():
             got_seq = model(i1, i2, iters=4)
         for a, b in zip(got_seq, want_seq):
-            assert _epe(a, b)[0] <= 0.01
+            assert _epe(a, b)[1] <= EPE_BOUND
     finally:
         raft_mod.CorrBlock, raft_mod.AlternateCorrBlock, raft_mod.RAFT.upsample_flow = old
 
@@ -137,7 +161,7 @@ def test_fused_motion_encoder_flow_matches_reference(ref, iters):
         mean, mx = _epe(_flow(model, i1, i2, iters), want)
         print(f"fused motion encoder, iters={iters}: EPE delta mean {mean:.2e} px, max {mx:.2e} px")
         assert calls["fused"] == iters
-        assert mean <= 0.01 and mx <= 0.05
+        assert mean <= EPE_BOUND  # fp16 tensor-core operands in convc1: a fast mode, max printed above
         preds = model(i1[:, :, :128, :256].contiguous(), i2[:, :, :128, :256].contiguous(), iters=2)  # autograd on
         assert calls["fused"] == iters and preds[-1].requires_grad  # the unfused pair ran, and it is differentiable
     finally:
@@ -161,12 +185,12 @@ def test_alternate_corr_dropin_flow_matches_reference(ref):
         raft_mod.AlternateCorrBlock = rcb.AlternateCorrBlock
         mean, mx = _epe(_flow(model_alt, i1, i2, 12), want)
         print(f"AlternateCorrBlock drop-in: EPE delta mean {mean:.2e} px, max {mx:.2e} px")
-        assert mean <= 0.01 and mx <= 0.05
+        assert mx <= EPE_BOUND
         raft_mod.AlternateCorrBlock = orig
         ref_corr.alt_cuda_corr = rcb.alt_cuda_corr  # what `import alt_cuda_corr` would have bound
         mean, mx = _epe(_flow(model_alt, i1, i2, 12), want)
         print(f"reference AlternateCorrBlock over our alt_cuda_corr: EPE delta mean {mean:.2e} px, max {mx:.2e} px")
-        assert mean <= 0.01 and mx <= 0.05
+        assert mx <= EPE_BOUND
     finally:
         raft_mod.AlternateCorrBlock = orig
 
@@ -195,4 +219,4 @@ def test_training_step_gradients_match_reference(ref):
     rel = ((g_our - g_ref).norm() / g_ref.norm()).item()
     print(f"loss ref {l_ref:.6f} ours {l_our:.6f}; fnet grad relative L2 error {rel:.2e}")
     assert abs(l_our - l_ref) <= 1e-3 * abs(l_ref)
-    assert rel <= 2e-2  # cuDNN's TF32 convolutions dominate the noise floor of this comparison
+    assert rel <= 2e-3  # TF32 is off in both arms; what remains is fp32 summation order (atomics in the backward kernels)

@@ -80,7 +80,7 @@ SHAPES = [(1, 20, 9, 11), (2, 96, 13, 22), (1, 256, 23, 39), (1, 136, 17, 8)]
 
 
 @pytest.mark.parametrize("pyr_dtype", ["f32", "f16"])
-@pytest.mark.parametrize("mode", ["bf16x3", "bf16", "fp32"])
+@pytest.mark.parametrize("mode", ["f16f8", "bf16x3", "bf16", "fp32"])
 @pytest.mark.parametrize("shape", SHAPES)
 def test_build_and_lookup_stay_inside_their_buffers(cabi, dev, shape, mode, pyr_dtype):
     if mode == "fp32" and pyr_dtype == "f16":

@@ -21,7 +21,7 @@ TOL = 1e-4
 GRAD_TOL = 2e-4
 BF16_TOL = 5e-3
 CONVC1_TOL = 1e-3  # fused lookup + convc1: fp16 tensor-core operands (section 9)
-PARITY_MODES = os.environ.get("RCB_TEST_MODES", "fp32,bf16x3").split(",")
+PARITY_MODES = os.environ.get("RCB_TEST_MODES", "fp32,bf16x3,f16f8").split(",")
 
 
 @pytest.fixture(scope="module")
@@ -141,12 +141,38 @@ def test_backward_accumulates_over_iterations(rcb, dev, orc, dims, mode):
     assert rel_err(f2.grad.cpu().numpy(), a2 + b2) < GRAD_TOL
 
 
+@pytest.mark.parametrize("mode", PARITY_MODES)
+def test_backward_vs_oracle_training_geometry(rcb, dev, orc, mode):
+    """BASELINE.json cfg5 geometry (FlyingChairs 368x496 -> 46x62, C = 256, r = 4, 4 levels), one frame pair, two GRU
+    iterations: dF1 / dF2 / dcoords against OracleCorrBlock.backward (what autograd yields through the reference
+    CorrBlock, train.py:212).  Q = 2852 = 23 query tiles, K = 23 k-blocks of the tcgen05 backward GEMMs."""
+    B, C, H, W, L, r = 1, 256, 46, 62, 4, 4
+    f1n, f2n, c0 = seeded(51, B, C, H, W, sigma=3.0)
+    _, _, c1 = seeded(52, B, C, H, W, sigma=3.0)
+    f1 = t(f1n, dev).requires_grad_(True)
+    f2 = t(f2n, dev).requires_grad_(True)
+    co0 = t(c0, dev).requires_grad_(True)
+    blk = rcb.CorrBlock(f1, f2, num_levels=L, radius=r, mode=mode)
+    o0, o1 = blk(co0), blk(t(c1, dev))
+    g0, g1 = cotangent(53, tuple(o0.shape)), cotangent(54, tuple(o1.shape))
+    (o0 * t(g0, dev)).sum().add((o1 * t(g1, dev)).sum()).backward()
+    ob = orc.OracleCorrBlock(f1n, f2n, L, r)
+    assert rel_err(o0.detach().cpu().numpy(), ob(c0)) < TOL
+    a1, a2, ac = ob.backward(c0, g0)
+    b1, b2, _ = ob.backward(c1, g1)
+    assert rel_err(f1.grad.cpu().numpy(), a1 + b1) < GRAD_TOL
+    assert rel_err(f2.grad.cpu().numpy(), a2 + b2) < GRAD_TOL
+    assert rel_err(co0.grad.cpu().numpy(), ac) < GRAD_TOL
+
+
 # ---------------------------------------------------------------------------------------------
 # (2) CPU oracle on seeded inputs
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("mode", PARITY_MODES)
 @pytest.mark.parametrize("shape", [(2, 64, 23, 39, 4, 4), (1, 128, 55, 128, 4, 3), (1, 256, 46, 62, 4, 4),
-                                   (3, 32, 9, 17, 2, 1), (1, 48, 16, 33, 3, 2)])
+                                   (3, 32, 9, 17, 2, 1), (1, 48, 16, 33, 3, 2),
+                                   # the full geometry of BASELINE.json cfg2 / cfg3 (C = 256, r = 4), one frame pair
+                                   (1, 256, 55, 128, 4, 4), (1, 256, 47, 156, 4, 4)])
 def test_corrblock_vs_oracle(rcb, dev, orc, shape, mode):
     B, C, H, W, L, r = shape
     f1, f2, coords = seeded(100 + H, B, C, H, W)

@@ -40,11 +40,53 @@ def _worker(rank, world, port, out):
               torch.nn.Parameter(torch.zeros(2, 2)), torch.nn.Parameter(torch.zeros(4))]
     for i, p in enumerate(params[:3]):
         p.grad = torch.full_like(p, float(rank + 1) * (i + 1))
+    if rank == 0:  # only one rank has a gradient for the last parameter (an unused branch on the other)
+        params[3].grad = torch.full_like(params[3], 8.0)
     launches = parallel.allreduce_grads(params, bucket_bytes=64, average=True)
     span = parallel.shard_range(9, world, rank)
-    out.put((rank, tmax, launches, [p.grad.clone() if p.grad is not None else None for p in params], span))
+    reducer_result = _reducer_case(rank, world)
+    out.put((rank, tmax, launches, [p.grad.clone() if p.grad is not None else None for p in params], span,
+             reducer_result))
     dist.barrier()
     dist.destroy_process_group()
+
+
+def _reducer_case(rank, world):
+    """GradBucketReducer (all-reduce launched from backward hooks, bucket by bucket) against a plain all-reduce of the
+    same local gradients; the middle layer is unused on rank 1, so one bucket has to be flushed by finish()."""
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(6, 16), torch.nn.Tanh(), torch.nn.Linear(16, 16), torch.nn.Tanh(),
+                              torch.nn.Linear(16, 3))
+    twin = torch.nn.Sequential(torch.nn.Linear(6, 16), torch.nn.Tanh(), torch.nn.Linear(16, 16), torch.nn.Tanh(),
+                               torch.nn.Linear(16, 3))
+    twin.load_state_dict(net.state_dict())
+    x = torch.randn(5, 6, generator=torch.Generator().manual_seed(100 + rank))
+
+    def fwd(m):
+        h = m[1](m[0](x))
+        if rank == 0:
+            h = m[3](m[2](h))
+        return m[4](h).square().sum()
+
+    red = parallel.GradBucketReducer(net.parameters(), bucket_bytes=256, average=True)
+    results = []
+    for step in range(2):  # state must reset between steps
+        net.zero_grad(set_to_none=True)
+        twin.zero_grad(set_to_none=True)
+        red.begin_step()
+        fwd(net).backward()
+        launched_in_backward = list(red.launch_order)
+        n = red.finish()
+        fwd(twin).backward()
+        for p in twin.parameters():
+            if p.grad is None:
+                p.grad = torch.zeros_like(p)
+            dist.all_reduce(p.grad)
+            p.grad /= world
+        err = max((a.grad - b.grad).abs().max().item() for a, b in zip(net.parameters(), twin.parameters()))
+        results.append((n, len(red.buckets), launched_in_backward, err))
+    red.remove()
+    return results
 
 
 def test_two_rank_gloo_allreduce_and_timing():
@@ -59,10 +101,18 @@ def test_two_rank_gloo_allreduce_and_timing():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    for rank, tmax, launches, grads, span in results:
+    for rank, tmax, launches, grads, span, reducer in results:
         assert tmax == [2.0, 5.0]
-        assert launches == 2  # 15*4 + 7*4 >= 64 bytes -> first bucket; the 2x2 tensor flushes at the end
+        assert launches == 2  # 15*4 + 7*4 >= 64 bytes -> first bucket; the two small tensors flush at the end
         for i in range(3):
             assert torch.allclose(grads[i], torch.full_like(grads[i], 1.5 * (i + 1)))  # mean of 1x and 2x
-        assert grads[3] is None
+        # a gradient that exists on one rank only is averaged against zeros, with identical bucket layouts on all ranks
+        assert torch.allclose(grads[3], torch.full_like(grads[3], 4.0))
+        for n, nbuckets, in_backward, err in reducer:
+            assert nbuckets >= 3 and n == nbuckets       # every bucket reduced exactly once per step
+            assert len(in_backward) >= 1                 # ... and at least the last layer's already during backward
+            assert in_backward == sorted(in_backward)    # buckets complete in reverse layer order
+            if rank == 1:
+                assert len(in_backward) < nbuckets       # the unused layer's bucket was flushed by finish()
+            assert err < 1e-6
     assert [r[4] for r in results] == [(0, 5), (5, 9)]

@@ -1,4 +1,5 @@
-"""Times rcb_corr_build (pack + main kernel) through the C ABI with preallocated buffers (no Python/torch
+"""(RCB_USE_DEBUG_LIB=1 + `python -m raft_optical_flow_b200.build --debug` for the RCB_TC_* hooks.)
+Times rcb_corr_build (pack + main kernel) through the C ABI with preallocated buffers (no Python/torch
 allocation inside the timed loop), CUDA events on the launching stream.
     python tools/time_build.py [--config cfg2] [--mode bf16x3] [--reps 20]"""
 import argparse, os, sys, time
@@ -73,14 +74,20 @@ if a.between != "none":
     ts = sorted(x.elapsed_time(y) * 1e3 for x, y in evs[2:])
     print(f"{a.config} {a.mode} between={a.between}: build median {ts[len(ts) // 2]:.1f} us, min {ts[0]:.1f}, max {ts[-1]:.1f}")
 if os.environ.get("RCB_TC_PROF") == "1":
-    prof = torch.zeros(16 * 148, dtype=torch.int64, device=dev)
+    prof = torch.zeros(16 * 148 + 20 * 148, dtype=torch.int64, device=dev)
     os.environ["RCB_TC_PROF_PTR"] = hex(prof.data_ptr())
     call()
     torch.cuda.synchronize()
     del os.environ["RCB_TC_PROF_PTR"]
-    pr = prof.view(148, 16).double()
+    pr = prof[:16 * 148].view(148, 16).double()
+    phases = ["wait_acc_full", "tmem_ld", "release_acc", "scale+pool", "wait_store_read", "staging+l2_store", "fence",
+              "pair_barrier", "tma_issue+commit", "level3"]
+    php = prof[16 * 148:].view(148, 2, 10).double().mean(0)
+    for b in range(2):
+        print(f"band {b} phases (mean cycles per CTA):", {n: int(php[b, i].item()) for i, n in enumerate(phases)})
     names = ["prod_total", "prod_wait_b_empty", "unused", "mma_total", "mma_wait_b_full", "mma_wait_acc_empty",
-             "mma_wait_a_full", "epi_total", "epi_wait_acc_full", "epi_wait_store_read", "epi_tmem_ld", "tiles", "pool_total", "pool_wait_acc_full"]
+             "mma_wait_a_full", "band0_total", "band0_wait_acc_full", "band0_wait_store_read", "tiles",
+             "band1_total", "band1_wait_acc_full", "band1_wait_store_read"]
     print("per-CTA mean cycles:", {n: int(pr[:, i].mean().item()) for i, n in enumerate(names)})
 print(f"{a.config} {a.mode} skip={os.environ.get('RCB_TC_DEBUG_SKIP','0')} nstage={os.environ.get('RCB_TC_NSTAGE','-')} "
       f"build {e0.elapsed_time(e1) / a.reps * 1e3:.1f} us (host enqueue {1e6 * (t1 - t0) / a.reps:.1f} us/call)")
