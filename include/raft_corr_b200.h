@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define RCB_ABI_VERSION 7
+#define RCB_ABI_VERSION 8
 #define RCB_MAX_LEVELS 4 /* core/raft.py:46-53 fixes corr_levels = 4 */
 #define RCB_MAX_RADIUS 4 /* core/raft.py:47,53: radius 3 (small) / 4 (full) */
 
@@ -101,6 +101,21 @@ RCB_API size_t rcb_corr_build_workspace_bytes(int B, int C, int H, int W, int mo
 RCB_API int rcb_corr_build(const float* fmap1, const float* fmap2, void* const* pyr, int B, int C, int H, int W,
                    int levels, int mode, int pyr_dtype, void* workspace, size_t workspace_bytes,
                    rcb_stream_t stream);
+
+/* ---- next row: the build split at its operand boundary ---------------------------------
+ * rcb_corr_build(fmap1, fmap2, ...) == rcb_corr_pack_fmaps + rcb_corr_build_packed (tensor-core modes only).
+ * rcb_corr_pack_fmaps consumes the feature encoder's output for the concatenated frame pair as ONE tensor
+ *   fmaps [2B, C, H, W] fp32 -- what fnet returns before torch.split (core/extractor.py:184-190; core/raft.py:178-182
+ *   then calls .float() on the two halves): the first B maps are the queries (fmap1), the last B the targets (fmap2)
+ *   -- and writes the tensor-core operands of `mode` into `packed` (rcb_corr_build_workspace_bytes(B, C, H, W, mode)
+ *   bytes, 128-byte aligned): per query pixel the image of its tensor-memory lane, per target patch ready-made
+ *   SWIZZLE_128B tile images.  A producer that emits this layout itself (a fused epilogue of the encoder's last
+ *   1x1 convolution, core/extractor.py:144) can skip the call; the layout is described in csrc/corr_build_tc.cu.
+ * rcb_corr_build_packed runs the volume + pyramid kernel on such operands (same B, C, H, W, mode). */
+RCB_API int rcb_corr_pack_fmaps(const float* fmaps, void* packed, size_t packed_bytes, int B, int C, int H, int W,
+                                int mode, rcb_stream_t stream);
+RCB_API int rcb_corr_build_packed(const void* packed, size_t packed_bytes, void* const* pyr, int B, int C, int H, int W,
+                                  int levels, int mode, int pyr_dtype, rcb_stream_t stream);
 
 /* ---- K2: fused multi-level window lookup ------------------------------------------------
  * Replaces CorrBlock.__call__ (core/corr.py:56-94) including bilinear_sampler

@@ -10,8 +10,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libraftcorr_b200.so")
 if os.environ.get("RCB_USE_DEBUG_LIB") == "1":  # timing / profiling hooks (tools/time_*.py); see build.py --debug
     LIB_PATH = os.path.join(HERE, "libraftcorr_b200_debug.so")
+if os.environ.get("RCB_LIB_VARIANT"):  # A/B builds of build.py --variant (debug-hook builds with compile-time switches)
+    LIB_PATH = os.path.join(HERE, f"libraftcorr_b200_{os.environ['RCB_LIB_VARIANT']}.so")
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 MAX_LEVELS = 4
 MAX_RADIUS = 4
 
@@ -46,6 +48,8 @@ SIGNATURES = {
     "rcb_pyramid_layout_query": (_i, [_i, _i, _i, _i, _i, ctypes.POINTER(PyramidLayout)]),
     "rcb_corr_build_workspace_bytes": (ctypes.c_size_t, [_i, _i, _i, _i, _i]),
     "rcb_corr_build": (_i, [_vp, _vp, ctypes.POINTER(_vp), _i, _i, _i, _i, _i, _i, _i, _vp, ctypes.c_size_t, _vp]),
+    "rcb_corr_pack_fmaps": (_i, [_vp, _vp, ctypes.c_size_t, _i, _i, _i, _i, _i, _vp]),
+    "rcb_corr_build_packed": (_i, [_vp, ctypes.c_size_t, ctypes.POINTER(_vp), _i, _i, _i, _i, _i, _i, _i, _vp]),
     "rcb_corr_lookup": (_i, [ctypes.POINTER(_vp), _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "rcb_corr_lookup_plan_bytes": (ctypes.c_size_t, []),
     "rcb_corr_lookup_plan_init": (_i, [_vp, ctypes.c_size_t, ctypes.POINTER(_vp), _i, _i, _i, _i, _i, _i]),
@@ -79,11 +83,14 @@ def lib():
                 f"{LIB_PATH} is missing: build it with `python -m raft_optical_flow_b200.build` "
                 "(nvcc, sm_100a).  raft_optical_flow_b200 has no CPU/PyTorch fallback.")
         handle = ctypes.CDLL(LIB_PATH)
+        variant = bool(os.environ.get("RCB_LIB_VARIANT"))  # A/B timing builds may be older revisions of the ABI
         for name, (res, args) in SIGNATURES.items():
+            if variant and not hasattr(handle, name):
+                continue
             fn = getattr(handle, name)  # AttributeError if the library does not export the ABI
             fn.restype = res
             fn.argtypes = args
-        if handle.rcb_abi_version() != ABI_VERSION:
+        if handle.rcb_abi_version() != ABI_VERSION and not variant:
             raise RuntimeError("libraftcorr_b200.so ABI version mismatch")
         _lib = handle
     return _lib

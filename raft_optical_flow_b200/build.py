@@ -39,13 +39,18 @@ def needs_build(lib=LIB):
     return any(os.path.getmtime(d) > os.path.getmtime(lib) for d in deps)
 
 
-def build(force=False, verbose=False, debug=False):
+def build(force=False, verbose=False, debug=False, variant=None, defines=()):
+    """variant="name" + defines=["-DRCB_X=1", ...] compiles libraftcorr_b200_<name>.so (a debug-hook build with
+    compile-time switches, for A/B timing inside one GPU session; select it with RCB_LIB_VARIANT=name)."""
     lib = DEBUG_LIB if debug else LIB
+    if variant:
+        lib = os.path.join(HERE, f"libraftcorr_b200_{variant}.so")
+        debug = True
     if not force and not needs_build(lib):
         return lib
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-DRCB_DEBUG"] if debug else []) + (["-Xptxas", "-v"] if verbose else []) + \
-        ["-o", lib] + sources()
+    cmd = [nvcc] + NVCC_FLAGS + (["-DRCB_DEBUG"] if debug else []) + list(defines) + \
+        (["-Xptxas", "-v"] if verbose else []) + ["-o", lib] + sources()
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
@@ -58,3 +63,6 @@ if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
     if "--debug" in sys.argv:
         print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, debug=True))
+    if "--variant" in sys.argv:
+        name = sys.argv[sys.argv.index("--variant") + 1]
+        print(build(force=True, verbose="-v" in sys.argv, variant=name, defines=[a for a in sys.argv if a.startswith("-D")]))

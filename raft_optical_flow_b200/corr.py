@@ -21,7 +21,7 @@ import torch.nn.functional as F
 
 from . import _cabi
 
-__all__ = ["CorrBlock", "AlternateCorrBlock", "PackedConvC1"]
+__all__ = ["CorrBlock", "AlternateCorrBlock", "PackedConvC1", "PackedFmaps"]
 
 DEFAULT_MODE = os.environ.get("RAFT_CORR_MODE", "f16f8")
 
@@ -150,19 +150,51 @@ class _LookupFn(torch.autograd.Function):
         return dco, dtoken, None
 
 
+class PackedFmaps:
+    """Tensor-core operands of the volume build, packed once from the feature encoder's output for the concatenated
+    frame pair (scope table 8f, f2): ``fmaps`` is the [2N, C, H, W] tensor fnet returns before ``torch.split``
+    (reference core/extractor.py:184-190, core/raft.py:178-182) -- first N maps = fmap1 (queries), last N = fmap2
+    (targets).  ``CorrBlock.from_packed(packed)`` then runs only the volume + pyramid kernel.  The operand layout
+    (rcb_corr_pack_fmaps) is what a fused epilogue of the encoder's last 1x1 convolution would have to emit."""
+
+    def __init__(self, fmaps, mode=None):
+        _check_cuda(fmaps, "fmaps")
+        if fmaps.dim() != 4 or fmaps.shape[0] % 2:
+            raise RuntimeError("fmaps must be the [2N, C, H, W] encoder output of the concatenated frame pair")
+        f = _prep(fmaps, "fmaps")
+        self.shape = (f.shape[0] // 2,) + tuple(f.shape[1:])
+        B, C, H, W = self.shape
+        self.mode = _cabi.BUILD_MODES[mode or DEFAULT_MODE]
+        if self.mode == _cabi.BUILD_FP32_SIMT or C > 256:
+            raise RuntimeError("packed operands exist for the tensor-core build modes only (C <= 256)")
+        lib = _cabi.lib()
+        self.nbytes = lib.rcb_corr_build_workspace_bytes(B, C, H, W, self.mode)
+        self.buf = torch.empty(self.nbytes, dtype=torch.uint8, device=f.device)
+        with torch.cuda.device(f.device):
+            _cabi.check(lib.rcb_corr_pack_fmaps(f.data_ptr(), self.buf.data_ptr(), self.nbytes, B, C, H, W, self.mode,
+                                                _stream(f)), "rcb_corr_pack_fmaps")
+
+
 class _State:
     """Everything one CorrBlock owns on the device."""
 
-    def __init__(self, f1, f2, levels, radius, mode, pyr_dtype):
-        B, C, H, W = f1.shape
+    def __init__(self, f1, f2, levels, radius, mode, pyr_dtype, packed=None):
+        B, C, H, W = f1.shape if packed is None else packed.shape
+        dev = f1.device if packed is None else packed.buf.device
         self.f1, self.f2, self.levels, self.radius, self.mode = f1, f2, levels, radius, mode
-        self.pyr = _Pyramid(B, H, W, levels, f1.device, pyr_dtype)
+        self.pyr = _Pyramid(B, H, W, levels, dev, pyr_dtype)
         self.dpyr = None
-        _build(f1, f2, levels, mode, self.pyr)
-        with torch.cuda.device(f1.device):
+        if packed is None:
+            _build(f1, f2, levels, mode, self.pyr)
+        else:
+            with torch.cuda.device(dev):
+                _cabi.check(_cabi.lib().rcb_corr_build_packed(packed.buf.data_ptr(), packed.nbytes, self.pyr.ptrs, B, C, H,
+                                                              W, levels, mode, pyr_dtype, _stream(packed.buf)),
+                            "rcb_corr_build_packed")
+        with torch.cuda.device(dev):
             self.plan = _cabi.LookupPlan(self.pyr.ptrs, B, H, W, levels, radius, pyr_dtype)
         self.out_channels = levels * (2 * radius + 1) ** 2
-        self.device_index = f1.device.index if f1.device.index is not None else torch.cuda.current_device()
+        self.device_index = dev.index if dev.index is not None else torch.cuda.current_device()
         self._lookup = _cabi.lib().rcb_corr_lookup_planned
 
     def lookup(self, coords):
@@ -222,6 +254,18 @@ class CorrBlock:
         if torch.is_grad_enabled() and (fmap1.requires_grad or fmap2.requires_grad):
             self._token = _BuildFn.apply(fmap1, fmap2, self._state)
 
+    @classmethod
+    def from_packed(cls, packed, num_levels=4, radius=4, pyramid_dtype="f32"):
+        """The block of a frame pair whose features were packed with ``PackedFmaps`` (inference: no autograd)."""
+        if not 1 <= num_levels <= _cabi.MAX_LEVELS or not 1 <= radius <= _cabi.MAX_RADIUS:
+            raise RuntimeError(f"num_levels must be in 1..{_cabi.MAX_LEVELS} and radius in 1..{_cabi.MAX_RADIUS}")
+        self = cls.__new__(cls)
+        self.num_levels, self.radius = num_levels, radius
+        pyr_dtype = {"f32": _cabi.F32, "f16": _cabi.F16}[pyramid_dtype]
+        self._state = _State(None, None, num_levels, radius, packed.mode, pyr_dtype, packed=packed)
+        self._token = None
+        return self
+
     @property
     def corr_pyramid(self):
         """List of num_levels tensors [N*H*W, 1, H_i, W_i] like the reference attribute (core/corr.py:38,46-54);
@@ -264,6 +308,82 @@ class CorrBlock:
         return pyr.level(0).reshape(B, H, W, 1, H, W)
 
 
+class _AltBuildFn(torch.autograd.Function):
+    """Autograd anchor of AlternateCorrBlock: like _BuildFn, a scalar token makes this node's backward run once, after
+    every call of the forward pass has accumulated its NHWC feature gradients in the block."""
+
+    @staticmethod
+    def forward(ctx, fmap1, fmap2, block):
+        ctx.block = block
+        return torch.zeros((), device=fmap1.device)
+
+    @staticmethod
+    def backward(ctx, _grad_token):
+        blk = ctx.block
+        B, C, H, W = blk._shape
+        dev = blk._f1n.device
+        if blk._df1n is None:
+            z = torch.zeros((B, C, H, W), dtype=torch.float32, device=dev)
+            return z, z.clone(), None
+        # fmap2's pooled levels fold back onto level 0: avg_pool2d backward (core/corr.py:159-160), floor mode
+        g2 = None
+        for l in range(blk.num_levels - 1, -1, -1):
+            cur = blk._df2n[l]
+            if g2 is not None:
+                up = g2.repeat_interleave(2, dim=1).repeat_interleave(2, dim=2) * 0.25
+                cur = cur.clone() if cur is not None else torch.zeros_like(blk._f2n[l])
+                cur[:, :up.shape[1], :up.shape[2]] += up
+            g2 = cur if cur is not None else torch.zeros_like(blk._f2n[l])
+        df1 = blk._df1n.permute(0, 3, 1, 2).contiguous()
+        df2 = g2.permute(0, 3, 1, 2).contiguous()
+        blk._df1n, blk._df2n = None, [None] * blk.num_levels  # a second backward pass starts from zero again
+        return df1, df2, None
+
+
+class _AltLookupFn(torch.autograd.Function):
+    """One AlternateCorrBlock call.  Backward = the extension's backward kernel per level (rcb_altcorr_backward,
+    replacing alt_cuda_corr.backward, correlation.cpp:36-48) with the TRUE coordinate gradient the reference kernel
+    leaves at zero (correlation_kernel.cu:307), which is what autograd through CorrBlock yields."""
+
+    @staticmethod
+    def forward(ctx, coords, token, block):
+        ctx.block = block
+        c = _prep(coords, "coords")
+        ctx.save_for_backward(c)
+        ctx.needs_f = token is not None and token.requires_grad
+        return block._forward(c)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        blk = ctx.block
+        (c,) = ctx.saved_tensors
+        B, C, H, W = blk._shape
+        rd2 = (2 * blk.radius + 1) ** 2
+        want_c = ctx.needs_input_grad[0]
+        lib = _cabi.lib()
+        scale = 1.0 / math.sqrt(C)
+        cn = c.permute(0, 2, 3, 1)  # [B, H, W, 2] like core/corr.py:174
+        dco = torch.zeros((B, H, W, 2), dtype=torch.float32, device=c.device) if want_c else None
+        with torch.cuda.device(c.device):
+            s = _stream(c)
+            for l in range(blk.num_levels):
+                cg = (grad_out[:, l * rd2:(l + 1) * rd2].float() * scale).reshape(B, 1, rd2, H, W).contiguous()
+                cl = (cn / float(2 ** l)).reshape(B, 1, H, W, 2).contiguous()  # core/corr.py:187
+                f2 = blk._f2n[l]
+                g1, g2, gc = torch.empty_like(blk._f1n), torch.empty_like(f2), torch.empty_like(cl)
+                _cabi.check(lib.rcb_altcorr_backward(blk._f1n.data_ptr(), f2.data_ptr(), cl.data_ptr(), cg.data_ptr(),
+                                                     g1.data_ptr(), g2.data_ptr(), gc.data_ptr(), B, 1, H, W,
+                                                     f2.shape[1], f2.shape[2], C, blk.radius, int(want_c), s),
+                            "rcb_altcorr_backward")
+                if ctx.needs_f:
+                    blk._df1n = g1 if blk._df1n is None else blk._df1n.add_(g1)
+                    blk._df2n[l] = g2 if blk._df2n[l] is None else blk._df2n[l].add_(g2)
+                if want_c:
+                    dco.add_(gc.reshape(B, H, W, 2), alpha=1.0 / float(2 ** l))
+        dtoken = torch.zeros((), device=c.device) if ctx.needs_f else None
+        return (dco.permute(0, 3, 1, 2).contiguous() if want_c else None), dtoken, None
+
+
 class AlternateCorrBlock:
     """On-the-fly correlation (reference core/corr.py:130-198): no Q x Q volume is ever stored; every call
     evaluates the (2r+2)^2 tap dot products of each query at each level from pooled fmap2 features."""
@@ -292,6 +412,12 @@ class AlternateCorrBlock:
             _cabi.check(_cabi.lib().rcb_altcorr_prepare(f1.data_ptr(), f2.data_ptr(), self._f1n.data_ptr(),
                                                         self._f2ptrs, B, C, H, W, num_levels, _stream(f1)),
                         "rcb_altcorr_prepare")
+        # autograd (the reference has none on this path: alt_cuda_corr.backward is never called from Python): gradients
+        # with respect to the feature maps accumulate here over the calls of one forward pass
+        self._df1n, self._df2n = None, [None] * num_levels
+        self._token = None
+        if torch.is_grad_enabled() and (fmap1.requires_grad or fmap2.requires_grad):
+            self._token = _AltBuildFn.apply(fmap1, fmap2, self)
 
     @property
     def pyramid(self):
@@ -307,8 +433,12 @@ class AlternateCorrBlock:
         return out
 
     def __call__(self, coords):
+        if torch.is_grad_enabled() and (self._token is not None or coords.requires_grad):
+            return _AltLookupFn.apply(coords, self._token, self)
+        return self._forward(_prep(coords, "coords"))
+
+    def _forward(self, c):
         B, C, H, W = self._shape
-        c = _prep(coords, "coords")
         if tuple(c.shape) != (B, 2, H, W):
             raise RuntimeError(f"coords shape {tuple(c.shape)} does not match the feature maps")
         rd = 2 * self.radius + 1

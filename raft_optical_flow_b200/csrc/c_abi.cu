@@ -53,6 +53,26 @@ int rcb_corr_build(const float* fmap1, const float* fmap2, void* const* pyr, int
   }
 }
 
+int rcb_corr_pack_fmaps(const float* fmaps, void* packed, size_t packed_bytes, int B, int C, int H, int W, int mode,
+                        rcb_stream_t stream) {
+  if (!fmaps || !packed || B <= 0 || C <= 0 || H <= 0 || W <= 0 || !aligned16(fmaps)) return RCB_ERR_INVALID_ARGUMENT;
+  if (mode != RCB_BUILD_BF16X3 && mode != RCB_BUILD_BF16 && mode != RCB_BUILD_F16F8) return RCB_ERR_UNSUPPORTED;
+  return launch_pack_tc(fmaps, fmaps + (size_t)B * C * H * W, B, C, H, W, mode, packed, packed_bytes,
+                        reinterpret_cast<cudaStream_t>(stream));
+}
+
+int rcb_corr_build_packed(const void* packed, size_t packed_bytes, void* const* pyr, int B, int C, int H, int W,
+                          int levels, int mode, int pyr_dtype, rcb_stream_t stream) {
+  if (!packed || !pyr || C <= 0) return RCB_ERR_INVALID_ARGUMENT;
+  if (mode != RCB_BUILD_BF16X3 && mode != RCB_BUILD_BF16 && mode != RCB_BUILD_F16F8) return RCB_ERR_UNSUPPORTED;
+  rcb_pyramid_layout lay;
+  int st = fill_layout(B, H, W, levels, pyr_dtype, &lay);
+  if (st != RCB_OK) return st;
+  for (int l = 0; l < levels; ++l)
+    if (!pyr[l] || !aligned16(pyr[l])) return RCB_ERR_INVALID_ARGUMENT;
+  return launch_build_tc_packed(packed, packed_bytes, pyr, lay, B, C, H, W, mode, reinterpret_cast<cudaStream_t>(stream));
+}
+
 int rcb_corr_lookup(const void* const* pyr, const float* coords, float* out, int B, int H, int W, int levels,
                     int radius, int pyr_dtype, rcb_stream_t stream) {
   if (!pyr || !coords || !out) return RCB_ERR_INVALID_ARGUMENT;

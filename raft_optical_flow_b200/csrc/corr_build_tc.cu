@@ -16,9 +16,13 @@
 //                        restriction (fp16 overflows beyond 65504).
 //     RCB_BUILD_BF16     hi parts only (fast mode, ~2.6e-3).
 //   main kernel   persistent, warp-specialised, 320 threads per CTA, one CTA per SM:
-//     warp 0      TMA producer: B tiles (an 8 x 16 PATCH of target pixels x 128 bytes of K; a 4-D box of the
-//                 [part*B, H, W, K] operand tensor, out-of-image rows/cols zero-filled) stream through an mbarrier
-//                 ring, two boxes per stage.
+//     warp 0      producer: B tiles (an 8 x 16 PATCH of target pixels x 128 bytes of K = a 16 KB box) stream through an
+//                 mbarrier ring, two boxes per stage.  The pack kernel writes the target operand as ready-made TILE
+//                 IMAGES -- per (batch, patch) the boxes of the tile's MMA schedule back to back, rows already in the
+//                 SWIZZLE_128B order the MMA descriptors expect, out-of-image targets as zeros -- so a stage is ONE
+//                 linear cp.async.bulk of 32 contiguous KB.  (Round 1 fetched each box as a 4-D tensor-map box of 128
+//                 rows x 128 B: the TMA unit then spends ~3.3 cycles per row, 1024 rows per tile, and the B stream
+//                 alone took 290 us of the kernel, profiles/r2b_build_anatomy_band_split.txt.)
 //     warp 1      MMA issuer: M = 128 queries x N = 128 targets per instruction, the A operand (queries) lives in
 //                 TENSOR MEMORY for a whole unit (TS form), B through SWIZZLE_128B K-major smem descriptors, fp32
 //                 accumulators in TMEM (double buffered).  The per-tile MMA schedule is a small table (Params::box).
@@ -30,20 +34,36 @@
 //                 of odd rows/cols needs no code: a level-k cell computed from a dropped row/col is itself outside
 //                 H_k x W_k, i.e. tile padding or a clipped tile), adds them to the pair's shared level-1 box, executes
 //                 ONE fence.proxy.async, meets its partner at a named barrier and issues its TMA stores (band 0 also
-//                 the level-1 box; band 1 reads the partner's level-1 rows back and finishes level 3).  Round 1 split
+//                 the level-1 box).  Band 1 then writes levels 2 and 3 for both: the two level-2 rows of a patch are
+//                 32 contiguous bytes of one tile, i.e. a FULL sector per query (band 0's row comes over through
+//                 shared memory) -- written as two 16-byte halves by two warps they cost ~30 us more.  Round 1 split
 //                 the warps by output LEVEL instead: the four level-0 warps then spent ~4000 cycles per tile in four
 //                 fence / wait / issue rounds and were, with the MMAs, the critical path (role counters in
-//                 profiles/r2_build_anatomy.txt) while the pooled-level warps idled and re-read the accumulator.
+//                 profiles/r2a_build_anatomy_round1_kernel.txt) while the pooled-level warps idled and re-read the
+//                 accumulator.  Levels 2/3 through TMA boxes of 32 / 16-byte rows were measured too: cheaper when the
+//                 stores run alone, slower in the full kernel (more traffic through the TMA unit that also feeds B).
 //     both        epilogue warps of a quarter also place the A operand in tensor memory (global -> registers ->
 //                 tcgen05.st) at the start of every unit, half of the columns each.
 //   work split    a unit = all patches of one (batch, 128-query tile); units go round-robin over the CTAs, which
 //                 therefore sweep the same batch's patches in step (B tiles are found in L2); the units left over
 //                 after the full rounds are cut along the patch sequence so the last round is short, not idle.
+//                 Patches are swept in vertical pairs, (0,0) (1,0) (0,1) (1,1) ...: the 2 x 2 patches that share a
+//                 128-byte line of level 2 then follow each other closely and the line is completed while it is still
+//                 in L2 (row-major order writes it in pieces a whole patch row apart: +20 us).
+//   what bounds it  the store path: this pattern (128-byte rows, one per query plane, 28 KB apart) is absorbed at
+//                 4.0-5.5 TB/s depending on the GPU of the pool (tools/probe/tma_store_probe2.cu; a plain fill reaches
+//                 7.3), the epilogue + stores alone take ~500 us at cfg2, and MMAs and B loads add 60-90 us of
+//                 interference on top (profiles/r2c..r2f).
 #include "rcb_common.cuh"
 #include "tcgen05_util.cuh"
 #include "tma_util.cuh"
 
 #include <cuda_fp8.h>
+
+// Build-time variant (A/B timing inside one GPU session: python -m raft_optical_flow_b200.build --variant NAME -D...)
+#ifndef RCB_PAIR_ORDER
+#define RCB_PAIR_ORDER 1     // patch sweep in vertical pairs: (0,0) (1,0) (0,1) (1,1) ... (0: row-major)
+#endif
 
 namespace rcb {
 
@@ -54,31 +74,31 @@ constexpr int PH = 8, PW = 16;   // target patch: 8 rows x 16 cols
 constexpr int BN = PH * PW;      // 128 targets per tile (TMEM columns)
 constexpr int BOX_K_BYTES = 128; // K extent of one B box in bytes (SWIZZLE_128B row): 64 x 16-bit or 128 x 8-bit
 constexpr int BOX_BYTES = BN * BOX_K_BYTES;  // 16 KB
-constexpr int BOXES_PER_STAGE = 2;
+constexpr int BOXES_PER_STAGE = 1;
 constexpr int STAGE_BYTES = BOXES_PER_STAGE * BOX_BYTES;
-constexpr int MAX_STAGE = 6;     // B ring depth is chosen at launch from the shared memory available
+constexpr int MAX_STAGE = 12;    // B ring depth is chosen at launch from the shared memory available
 constexpr int MAX_ACC = 4;       // TMEM accumulator buffers (128 columns each); count chosen at launch
 constexpr int MAX_BOX = 8;       // B boxes per tile (C <= 256)
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int THREADS = 32 * (2 + NUM_EPI_WARPS);
 constexpr int STG0_BYTES = 8192;  // per epilogue warp: the band's two level-0 boxes
-constexpr int STG1_BYTES = 8192;  // per lane quarter: the level-1 box, double buffered by tile parity
+constexpr int STG1_BYTES = 4096;  // per lane quarter: the level-1 box both warps of the pair fill
+constexpr int XCH_BYTES = 512;    // per lane quarter: band 0's level-2 row for its partner (16 bytes per query)
 
 // Dynamic shared memory (all tile buffers 1024-byte aligned for the swizzle atoms):
-//   [b_off, +nstage * 32 KB)   B ring
+//   [b_off, +nstage * 16 KB)   B ring -- as deep as the rest allows (9 boxes): the kernel is latency-bound on the B
+//                              stream while the store path is saturated (4 boxes: 900 us, 7: 665 us at cfg2)
 //   [stg0_off, +8 * 8 KB)      level-0 staging, one band per epilogue warp
-//   [stg1_off, +4 * 8 KB)      level-1 staging, two boxes per lane quarter
+//   [stg1_off, +4 * 4 KB)      level-1 staging, one box per lane quarter
+//   [xch_off, +4 * 512 B)      level-2 rows handed from band 0 to band 1
 //   [bar_off, +1 KB)           mbarriers + TMEM base slot
 constexpr int SMEM_BUDGET = 227 * 1024;
 constexpr int BAR_BYTES = 1024;
 
 enum MmaKind { KIND_F16 = 0, KIND_F8 = 1 };
 
-// One B box of a tile and the MMAs it feeds (four K steps of 32 bytes each).
+// One B box of a tile (box j of the tile image) and the MMAs it feeds (four K steps of 32 bytes each).
 struct BoxDesc {
-  int map8;     // 0: 16-bit operand tensor (map_b16), 1: 8-bit operand tensor (map_b8)
-  int part;     // leading index of the operand tensor is part * B + batch
-  int kcoord;   // first K element of the box
   int a_col0;   // TMEM column of the A operand this box meets
   int a_col1;   // a second A operand for the same box (bf16x3: B_hi also meets A_lo), -1 = none
   int kind;     // MmaKind
@@ -95,11 +115,12 @@ struct Params {
   int full_rounds;  // rounds in which every CTA sweeps all patches of one (batch, query tile) unit
   int tail_pieces, tail_split, tail_len;  // left-over units: cut into tail_split ranges of tail_len patches
   float scale;      // 1 / sqrt(C)
-  int nstage, b_off, stg0_off, stg1_off, bar_off;  // shared memory carve-up (bytes)
+  int nstage, b_off, stg0_off, stg1_off, xch_off, bar_off;  // shared memory carve-up (bytes)
   int f16;                              // pyramid stored as fp16 (tiles of 4 rows x 8 columns), else fp32 (4 x 4)
   int nacc, acc_col0;                   // TMEM: accumulator count, first accumulator column
   int a_words;                          // 32-bit words of one packed A row = TMEM columns of the A operand
   const uint32_t* a_pack;               // packed A operand image, [B][Q][a_words]
+  const unsigned char* b_img;           // packed B tile images, [B][npatch][nbox][128 targets][128 B], pre-swizzled
   int nbox;
   BoxDesc box[MAX_BOX];
   float* pyr[RCB_MAX_LEVELS];           // (fp16 pyramids: the same pointers, reinterpreted)
@@ -163,43 +184,63 @@ RCB_DEVINL void named_bar_sync(uint32_t id, uint32_t nthreads) {
 }
 
 // ---- operand packing -----------------------------------------------------------------------
-// Where the operands of ONE feature map go (byte offsets; rows are per pixel).
-struct PackDst {
-  unsigned char* p16;            // 16-bit hi part (bf16 or fp16), 2 bytes per channel
-  long long row16, batch16;      // bytes per pixel / per batch element
-  long long lo16_off;            // 16-bit lo part at p16 + lo16_off (bf16x3), < 0: none
-  unsigned char* p8;             // 8-bit parts (f16f8), 1 byte per channel: e4m3(hi); nullptr: none
-  long long row8, batch8;
-  long long lo8_off;             // e4m3(lo * 2^12) at p8 + lo8_off
+// Where the operands go.  Queries (fmap1, the A operand): one row of a_row bytes per pixel = the image of the
+// pixel's TMEM lane, [hi16 | lo16] (bf16x3) or [hi16 | e4m3(hi) | e4m3(lo * 2^12)] (f16f8).  Targets (fmap2, the B
+// operand): tile images -- for every (batch, patch) the tile's boxes back to back, a box = 128 targets (row n =
+// patch row * 16 + patch column) x 128 bytes of K with the 16-byte chunks of row n XOR-swizzled by n & 7 (the
+// SWIZZLE_128B shared-memory layout), so the main kernel fetches a stage with one linear bulk copy.
+struct PackParams {
+  unsigned char* a_img;
+  long long a_row;               // bytes per query row
+  int a_lo16, a_hi8, a_lo8;      // byte offsets inside a row (a_lo16 < 0: no 16-bit lo part)
+  unsigned char* b_img;
+  int nbox, pcols, npatch, Hp, Wp;  // boxes per tile; patch grid; padded target grid (multiples of 8 x 16)
+  int box16_hi[4], box16_lo[4];  // box index of the 16-bit k-block kb (64 channels each); lo: bf16x3 only
+  int box8_hi[2], box8_lo[2];    // box index of the 8-bit k-block k8 (128 channels each); f16f8 only
   int K16, K8;                   // padded channel counts of the two operand widths
 };
 
-// in  [2 maps][B][C][Q] fp32 (two separate base pointers);  out: see PackDst, zero padded beyond C.
-// CTA = 64 channels x 64 queries: coalesced 8-byte loads along q into a padded fp32 tile, then every thread turns
-// 8 channels of one query into one 16-byte store per 16-bit part (8 lanes cover the 128 bytes of a query's k-block)
-// and one 8-byte store per 8-bit part.
+// in  [2 maps][B][C][Q] fp32 (two separate base pointers), zero padded beyond C and outside the image.
+// CTA = 64 channels x 64 pixels (queries: pixels of the image; targets: pixels of the PADDED grid): coalesced
+// loads along the row into a padded fp32 tile, then every thread turns 8 channels of one pixel into one 16-byte
+// store per 16-bit part (8 lanes cover the 128 bytes of a pixel's k-block) and one 8-byte store per 8-bit part.
 template <bool F8>
 __global__ void __launch_bounds__(256)
-pack_operands_kernel(const float* __restrict__ f1, const float* __restrict__ f2, const PackDst d0, const PackDst d1,
-                     int B, int C, int Q) {
+pack_operands_kernel(const float* __restrict__ f1, const float* __restrict__ f2, const __grid_constant__ PackParams d,
+                     int B, int C, int H, int W) {
   __shared__ float tile[64][65];  // odd pitch: the column reads below are at most 2-way bank-conflicted
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int map = blockIdx.z / B, b = blockIdx.z % B;
-  const float* in = (map == 0 ? f1 : f2) + (long long)b * C * Q;
-  const PackDst& d = map == 0 ? d0 : d1;
+  const int Q = H * W;
+  const int npix = map == 0 ? Q : d.Hp * d.Wp;  // pixel space of this map
   const int q0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
-  const bool even_q = (Q & 1) == 0;
+  if (q0 >= npix) return;
+  const float* in = (map == 0 ? f1 : f2) + (long long)b * C * Q;
+  // source offsets of this lane's two pixels (-1: outside the image)
+  int s0, s1;
+  {
+    const int i0 = q0 + 2 * lane, i1 = i0 + 1;
+    if (map == 0) {
+      s0 = i0 < Q ? i0 : -1;
+      s1 = i1 < Q ? i1 : -1;
+    } else {
+      const int y0 = i0 / d.Wp, x0 = i0 - y0 * d.Wp, y1 = i1 / d.Wp, x1 = i1 - y1 * d.Wp;
+      s0 = (y0 < H && x0 < W) ? y0 * W + x0 : -1;
+      s1 = (y1 < H && x1 < W) ? y1 * W + x1 : -1;
+    }
+  }
+  const bool pair = s0 >= 0 && s1 == s0 + 1 && (s0 & 1) == 0 && (Q & 1) == 0;  // one aligned 8-byte load
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    const int c = warp * 8 + i, cc = c0 + c, q = q0 + 2 * lane;
+    const int c = warp * 8 + i, cc = c0 + c;
     float2 v = make_float2(0.f, 0.f);
     if (cc < C) {
-      const float* src = in + (long long)cc * Q + q;
-      if (even_q && q + 1 < Q) {
-        v = __ldg(reinterpret_cast<const float2*>(src));  // rows start 8-byte aligned when Q is even
+      const float* src = in + (long long)cc * Q;
+      if (pair) {
+        v = __ldg(reinterpret_cast<const float2*>(src + s0));
       } else {
-        if (q < Q) v.x = __ldg(src);
-        if (q + 1 < Q) v.y = __ldg(src + 1);
+        if (s0 >= 0) v.x = __ldg(src + s0);
+        if (s1 >= 0) v.y = __ldg(src + s1);
       }
     }
     tile[c][2 * lane] = v.x;
@@ -210,11 +251,39 @@ pack_operands_kernel(const float* __restrict__ f1, const float* __restrict__ f2,
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
     const int ql = warp * 8 + i * 4 + (lane >> 3), q = q0 + ql;
-    if (q >= Q) continue;
+    if (q >= npix) continue;
     const int ch = c0 + 8 * cg;
     float x[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) x[j] = tile[8 * cg + j][ql];
+    // destinations: queries -> a row of the A image; targets -> row n of the patch's boxes
+    unsigned char *d16_hi = nullptr, *d16_lo = nullptr, *d8_hi = nullptr, *d8_lo = nullptr;
+    if (map == 0) {
+      unsigned char* row = d.a_img + ((long long)b * Q + q) * d.a_row;
+      if (ch < d.K16) {
+        d16_hi = row + ch * 2;
+        if (d.a_lo16 >= 0) d16_lo = row + d.a_lo16 + ch * 2;
+      }
+      if (F8) {
+        d8_hi = row + d.a_hi8 + ch;
+        d8_lo = row + d.a_lo8 + ch;
+      }
+    } else {
+      const int yp = q / d.Wp, xp = q - yp * d.Wp;
+      const int n = (yp & 7) * 16 + (xp & 15);
+      unsigned char* tb = d.b_img + (((long long)b * d.npatch + (yp >> 3) * d.pcols + (xp >> 4)) * d.nbox) * 16384 +
+                          n * 128;
+      if (ch < d.K16) {
+        const int kb = ch >> 6, off = ((((ch & 63) >> 3) ^ (n & 7)) << 4);
+        d16_hi = tb + d.box16_hi[kb] * 16384 + off;
+        if (d.box16_lo[kb] >= 0) d16_lo = tb + d.box16_lo[kb] * 16384 + off;
+      }
+      if (F8) {
+        const int k8 = ch >> 7, off = ((((ch & 127) >> 4) ^ (n & 7)) << 4) + (ch & 15);
+        d8_hi = tb + d.box8_hi[k8] * 16384 + off;
+        d8_lo = tb + d.box8_lo[k8] * 16384 + off;
+      }
+    }
     if (!F8) {
       __nv_bfloat162 hi[4], lo[4];
 #pragma unroll
@@ -224,13 +293,12 @@ pack_operands_kernel(const float* __restrict__ f1, const float* __restrict__ f2,
         lo[j] = __halves2bfloat162(__float2bfloat16_rn(x[2 * j] - __bfloat162float(h0)),
                                    __float2bfloat16_rn(x[2 * j + 1] - __bfloat162float(h1)));
       }
-      unsigned char* dst = d.p16 + (long long)b * d.batch16 + (long long)q * d.row16 + ch * 2;
-      *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(hi);
-      if (d.lo16_off >= 0) *reinterpret_cast<uint4*>(dst + d.lo16_off) = *reinterpret_cast<const uint4*>(lo);
+      if (d16_hi) *reinterpret_cast<uint4*>(d16_hi) = *reinterpret_cast<const uint4*>(hi);
+      if (d16_lo) *reinterpret_cast<uint4*>(d16_lo) = *reinterpret_cast<const uint4*>(lo);
     } else {
       // hi = fp16(x) (the full-rate pass), and for the cross terms e4m3(hi) and e4m3((x - hi) * 2^12):
-      // x - hi is exact in fp32 and at most half an fp16 ulp of x, so the scaled lo part is at most |x| / 2^... in
-      // magnitude (no overflow) and keeps ~4 significant bits, all that 2^-12-weighted terms need
+      // x - hi is exact in fp32 and at most half an fp16 ulp of x, so the scaled lo part never exceeds |x| in
+      // magnitude (no overflow where hi fits) and keeps ~4 significant bits, all that 2^-12-weighted terms need
       __half2 hi[4];
       uint32_t h8[2], l8[2];
 #pragma unroll
@@ -248,14 +316,18 @@ pack_operands_kernel(const float* __restrict__ f1, const float* __restrict__ f2,
           l8[j >> 1] = l;
         }
       }
-      if (ch < d.K16)
-        *reinterpret_cast<uint4*>(d.p16 + (long long)b * d.batch16 + (long long)q * d.row16 + ch * 2) =
-            *reinterpret_cast<const uint4*>(hi);
-      unsigned char* dst8 = d.p8 + (long long)b * d.batch8 + (long long)q * d.row8 + ch;
-      *reinterpret_cast<uint2*>(dst8) = make_uint2(h8[0], h8[1]);
-      *reinterpret_cast<uint2*>(dst8 + d.lo8_off) = make_uint2(l8[0], l8[1]);
+      if (d16_hi) *reinterpret_cast<uint4*>(d16_hi) = *reinterpret_cast<const uint4*>(hi);
+      *reinterpret_cast<uint2*>(d8_hi) = make_uint2(h8[0], h8[1]);
+      *reinterpret_cast<uint2*>(d8_lo) = make_uint2(l8[0], l8[1]);
     }
   }
+}
+
+// shared::cta <- global linear bulk copy, completion counted in bytes on an mbarrier
+RCB_DEVINL void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
 }
 
 // 8 floats -> 8 fp16 (round to nearest even) in one 16-byte vector
@@ -279,9 +351,28 @@ struct Segment {
   int b, mt, p_begin, p_end;
 };
 
+// Position i of the patch sweep -> patch (py, px).  Vertical pairs: the four patches (2 x 2) that share a 128-byte
+// line of level 2 are swept within four consecutive tiles, so the line is completed while it is still in L2 instead
+// of being written in four pieces a whole patch row apart (each piece evicted on its own by the 2 GB stream).
+RCB_DEVINL void sweep_to_patch(int i, int prows, int pcols, int& py, int& px) {
+#if RCB_PAIR_ORDER
+  const int full = (prows >> 1) * 2 * pcols;  // sweep positions inside complete row pairs
+  if (i < full) {
+    const int rp = i / (2 * pcols), w = i - rp * 2 * pcols;
+    px = w >> 1;
+    py = 2 * rp + (w & 1);
+  } else {
+    py = prows - 1;
+    px = i - full;
+  }
+#else
+  py = i / pcols;
+  px = i - py * pcols;
+#endif
+}
+
 __global__ void __launch_bounds__(THREADS, 1)
-build_tc_kernel(const __grid_constant__ CUtensorMap map_b16, const __grid_constant__ CUtensorMap map_b8,
-                const __grid_constant__ CUtensorMap map_l0, const __grid_constant__ CUtensorMap map_l1,
+build_tc_kernel(const __grid_constant__ CUtensorMap map_l0, const __grid_constant__ CUtensorMap map_l1,
                 const __grid_constant__ Params p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const uint32_t smem_base = smem_u32(smem);
@@ -360,20 +451,19 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_b16, const __grid_consta
     for (int si = 0; si < nseg; ++si) {
       const Segment sg = segment(si);
       for (int pi = sg.p_begin; pi < sg.p_end; ++pi) {
-        const int py = pi / p.pcols, px = pi % p.pcols;
+        int py, px;
+        sweep_to_patch(pi, p.prows, p.pcols, py, px);
+        const unsigned char* tile_img = p.b_img + ((long long)sg.b * p.npatch + py * p.pcols + px) * p.nbox * BOX_BYTES;
         for (int j = 0; j < p.nbox; j += BOXES_PER_STAGE) {
           mbar_wait_t(b_empty(s), ph ^ 1, pw0);
           if (elect_one()) {
             const int nbox = min(BOXES_PER_STAGE, p.nbox - j);
             if (RCB_SKIP(p, 16)) {
               mbar_arrive(b_full(s));
-            } else {
+            } else {  // the stage's boxes are contiguous in the tile image: one linear copy
               mbar_expect_tx(b_full(s), (uint32_t)(nbox * BOX_BYTES));
-              for (int i = 0; i < nbox; ++i) {
-                const BoxDesc& bx = p.box[j + i];
-                tma_load_4d(smem_base + p.b_off + s * STAGE_BYTES + i * BOX_BYTES, bx.map8 ? &map_b8 : &map_b16,
-                            b_full(s), bx.kcoord, px * PW, py * PH, bx.part * p.B + sg.b);
-              }
+              bulk_load(smem_base + p.b_off + s * STAGE_BYTES, tile_img + (long long)j * BOX_BYTES,
+                        (uint32_t)(nbox * BOX_BYTES), b_full(s));
             }
           }
           __syncwarp();
@@ -459,9 +549,11 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_b16, const __grid_consta
     const int band = ew >> 2;             // patch rows 4 * band .. 4 * band + 3
     const int quarter = warp & 3;         // TMEM lane quarter this warp may access; warps (w, w + 4) form a pair
     const int lane_q = quarter * 32;
-    const uint32_t pair_bar = 1 + quarter;  // named barrier of the pair (barrier 0 is __syncthreads)
+    // named barriers of the pair (barrier 0 is __syncthreads): "the shared boxes may be overwritten" / "are complete"
+    const uint32_t bar_free = 1 + quarter, bar_done = 5 + quarter;
     unsigned char* stg0 = smem + p.stg0_off + ew * STG0_BYTES;
-    unsigned char* stg1 = smem + p.stg1_off + quarter * STG1_BYTES;
+    unsigned char* sb1 = smem + p.stg1_off + quarter * STG1_BYTES;
+    unsigned char* xch = smem + p.xch_off + quarter * XCH_BYTES;
     const int swz = lane & 7;             // SWIZZLE_128B: 16-byte chunk c of row `lane` sits at chunk c ^ (lane & 7)
     int buf = 0;
     uint32_t aph = 0;
@@ -509,7 +601,8 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_b16, const __grid_consta
         if (lane == 0) mbar_arrive(a_full);
       }
       for (int pi = sg.p_begin; pi < sg.p_end; ++pi, ++tile) {
-        const int py = pi / p.pcols, px = pi % p.pcols;
+        int py, px;
+        sweep_to_patch(pi, p.prows, p.pcols, py, px);
         const int y0 = py * PH, x0 = px * PW;
         PH_START();
         mbar_wait_t(acc_full(buf), aph, pw0);
@@ -548,12 +641,15 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_b16, const __grid_consta
         const bool l0_ok = yy < p.H && q_w < p.Q;  // warp-uniform (x0 < W always holds)
         const int y1 = y0 >> 1, x1 = x0 >> 1;
         const bool l1_ok = p.levels > 1 && y1 < p.Hl[1] && x1 < p.Wl[1] && q_w < p.Q;  // the same in both warps of a pair
-        unsigned char* sb1 = stg1 + (tile & 1) * (STG1_BYTES / 2);
+        const int y2 = (y0 >> 2) + band, x2 = x0 >> 2;  // this band's level-2 row; x2 is a multiple of 4
         PH_MARK(3);
-        // every bulk store this lane-0 issued so far has read its staging buffer (they are one tile old)
+        // every bulk store this lane 0 issued so far has read its staging buffer (they are one tile old); after the
+        // pair's first barrier that also holds for the level-1 box band 0 issued, and band 1 has read the last
+        // level-2 row it was handed -- both shared buffers may be overwritten
         if (lane == 0) tma_store_wait_read<0>();
         __syncwarp();
         PH_MARK(4);
+        named_bar_sync(bar_free, 64);
         if (!p.f16) {
           // ---- fp32 pyramid: the band is four 4x4 tiles = 256 contiguous bytes per query = two boxes
           if (l0_ok && !RCB_SKIP(p, 8)) {
@@ -580,13 +676,6 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_b16, const __grid_consta
                   make_float4(l1b[4 * t], l1b[4 * t + 1], l1b[4 * t + 2], l1b[4 * t + 3]);
             }
           }
-          if (p.levels > 2 && q_ok && !RCB_SKIP(p, 4)) {
-            // level 2: this band's row of the 2 x 4 block = one 16-byte tile row (x2 is a multiple of 4)
-            const int y2 = (y0 >> 2) + band, x2 = x0 >> 2;
-            if (y2 < p.Hl[2] && x2 < p.Wl[2])
-              *reinterpret_cast<float4*>(p.pyr[2] + bq * p.ps[2] + tile_off(y2, x2, p.tx[2])) =
-                  make_float4(l2[0], l2[1], l2[2], l2[3]);
-          }
         } else {
           // ---- fp16 pyramid (tiles of 4 rows x 8 halfs): the band is two tiles = 128 bytes per query = ONE box; the
           // means are formed from the fp32 values and rounded once
@@ -609,23 +698,15 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_b16, const __grid_consta
             *reinterpret_cast<uint4*>(sb1 + lane * 64 + (((2 * band + 1) ^ s64) << 4)) =
                 pack_half8(l1b[0], l1b[1], l1b[2], l1b[3], l1b[4], l1b[5], l1b[6], l1b[7]);
           }
-          // band 0 hands its fp32 level-2 row to its partner (for level 3) behind the 2 KB level-1 box
-          if (band == 0) *reinterpret_cast<float4*>(sb1 + 2048 + lane * 16) = make_float4(l2[0], l2[1], l2[2], l2[3]);
-          if (p.levels > 2 && q_ok && !RCB_SKIP(p, 4)) {
-            const int y2 = (y0 >> 2) + band, x2 = x0 >> 2;  // x2 a multiple of 4: one 8-byte half row of a tile
-            if (y2 < p.Hl[2] && x2 < p.Wl[2]) {
-              const __half2 a0 = __floats2half2_rn(l2[0], l2[1]), a1 = __floats2half2_rn(l2[2], l2[3]);
-              *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(p.pyr[2]) + bq * p.ps[2] + tile_off_h(y2, x2, p.tx[2])) =
-                  make_uint2(*reinterpret_cast<const uint32_t*>(&a0), *reinterpret_cast<const uint32_t*>(&a1));
-            }
-          }
         }
+        // band 0 hands its (fp32) level-2 row to its partner, which writes levels 2 and 3 for both
+        if (band == 0) *reinterpret_cast<float4*>(xch + lane * 16) = make_float4(l2[0], l2[1], l2[2], l2[3]);
         PH_MARK(5);
         // one proxy fence per tile and warp, then the pair meets: band 0 issues the level-1 box both have written
         fence_proxy_async_smem();
         __syncwarp();
         PH_MARK(6);
-        named_bar_sync(pair_bar, 64);
+        named_bar_sync(bar_done, 64);
         PH_MARK(7);
         if (lane == 0) {
           if (l0_ok && !RCB_SKIP(p, 1)) {
@@ -642,29 +723,29 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_b16, const __grid_consta
         }
         __syncwarp();
         PH_MARK(8);
-        if (band == 1 && p.levels > 3 && q_ok && !RCB_SKIP(p, 4)) {
-          // level 3 = mean of the patch's 2 x 4 level-2 block, two values: the partner's level-2 row comes back from
-          // shared memory (fp32: recomputed from its level-1 rows in the box with the same expression, bit for bit)
-          const int y3 = y0 >> 3, x3 = x0 >> 3;  // x3 is even: both values sit in one tile row
-          if (y3 < p.Hl[3] && x3 < p.Wl[3]) {
-            float m2[4];
+        if (band == 1 && p.levels > 2 && q_ok && !RCB_SKIP(p, 4)) {
+          // levels 2 and 3 of the patch.  Level 2: rows y2 - 1 (band 0) and y2 of the 2 x 4 block are 32 contiguous
+          // bytes of one fp32 tile -- a full sector per query; level 3 = mean of the block, two values.
+          const float4 u = *reinterpret_cast<const float4*>(xch + lane * 16);
+          if ((y2 - 1) < p.Hl[2] && x2 < p.Wl[2]) {
             if (!p.f16) {
-              float pa[8], pb[8];
-#pragma unroll
-              for (int t = 0; t < 2; ++t) {
-                const float4 u = *reinterpret_cast<const float4*>(sb1 + lane * 128 + (((t * 4) ^ swz) << 4));
-                const float4 v = *reinterpret_cast<const float4*>(sb1 + lane * 128 + (((t * 4 + 1) ^ swz) << 4));
-                pa[4 * t] = u.x; pa[4 * t + 1] = u.y; pa[4 * t + 2] = u.z; pa[4 * t + 3] = u.w;
-                pb[4 * t] = v.x; pb[4 * t + 1] = v.y; pb[4 * t + 2] = v.z; pb[4 * t + 3] = v.w;
-              }
-#pragma unroll
-              for (int j = 0; j < 4; ++j) m2[j] = ((pa[2 * j] + pa[2 * j + 1]) + (pb[2 * j] + pb[2 * j + 1])) * 0.25f;
-            } else {
-              const float4 u = *reinterpret_cast<const float4*>(sb1 + 2048 + lane * 16);
-              m2[0] = u.x; m2[1] = u.y; m2[2] = u.z; m2[3] = u.w;
+              float* t2 = p.pyr[2] + bq * p.ps[2] + tile_off(y2 - 1, x2, p.tx[2]);
+              *reinterpret_cast<float4*>(t2) = u;
+              *reinterpret_cast<float4*>(t2 + 4) = make_float4(l2[0], l2[1], l2[2], l2[3]);
+            } else {  // tiles of 4 rows x 8 halfs: the two rows are 8 bytes each, 16 bytes apart
+              __half* t2 = reinterpret_cast<__half*>(p.pyr[2]) + bq * p.ps[2] + tile_off_h(y2 - 1, x2, p.tx[2]);
+              const __half2 a0 = __floats2half2_rn(u.x, u.y), a1 = __floats2half2_rn(u.z, u.w);
+              const __half2 b0 = __floats2half2_rn(l2[0], l2[1]), b1 = __floats2half2_rn(l2[2], l2[3]);
+              *reinterpret_cast<uint2*>(t2) =
+                  make_uint2(*reinterpret_cast<const uint32_t*>(&a0), *reinterpret_cast<const uint32_t*>(&a1));
+              *reinterpret_cast<uint2*>(t2 + 8) =
+                  make_uint2(*reinterpret_cast<const uint32_t*>(&b0), *reinterpret_cast<const uint32_t*>(&b1));
             }
-            const float a = ((m2[0] + m2[1]) + (l2[0] + l2[1])) * 0.25f;
-            const float c = ((m2[2] + m2[3]) + (l2[2] + l2[3])) * 0.25f;
+          }
+          const int y3 = y0 >> 3, x3 = x0 >> 3;  // x3 is even: both values sit in one tile row
+          if (p.levels > 3 && y3 < p.Hl[3] && x3 < p.Wl[3]) {
+            const float a = ((u.x + u.y) + (l2[0] + l2[1])) * 0.25f;
+            const float c = ((u.z + u.w) + (l2[2] + l2[3])) * 0.25f;
             if (!p.f16)
               *reinterpret_cast<float2*>(p.pyr[3] + bq * p.ps[3] + tile_off(y3, x3, p.tx[3])) = make_float2(a, c);
             else
@@ -702,82 +783,120 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_b16, const __grid_consta
 
 static int padded(int C, int to) { return (C + to - 1) / to * to; }
 
-// Operand workspace: [A image | 16-bit B tensor | 8-bit B tensor], each part 256-byte aligned, plus slack
+// Operand workspace: [A image | B tile images], each part 256-byte aligned
 struct WsLayout {
-  int K16, K8, parts16, a_words;
-  size_t a_bytes, b16_bytes, b8_bytes, total;
+  int K16, K8, parts16, a_words, nbox, pcols, prows;
+  size_t a_bytes, b_bytes, total;
 };
 static WsLayout ws_layout(int B, int C, int H, int W, int mode) {
   WsLayout w{};
-  const size_t n = (size_t)B * H * W;
   w.K16 = padded(C, 64);
   w.K8 = mode == RCB_BUILD_F16F8 ? padded(C, 128) : 0;
   w.parts16 = mode == RCB_BUILD_BF16X3 ? 2 : 1;
   w.a_words = w.parts16 * w.K16 / 2 + w.K8 / 2;
+  w.nbox = w.parts16 * w.K16 / 64 + 2 * (w.K8 / 128);
+  w.pcols = (W + tc::PW - 1) / tc::PW;
+  w.prows = (H + tc::PH - 1) / tc::PH;
   auto up = [](size_t x) { return (x + 255) / 256 * 256; };
-  w.a_bytes = up(n * w.a_words * 4);
-  w.b16_bytes = up(n * w.parts16 * w.K16 * 2);
-  w.b8_bytes = up(n * 2 * w.K8);
-  w.total = w.a_bytes + w.b16_bytes + w.b8_bytes;
+  w.a_bytes = up((size_t)B * H * W * w.a_words * 4);
+  w.b_bytes = up((size_t)B * w.pcols * w.prows * w.nbox * tc::BOX_BYTES);
+  w.total = w.a_bytes + w.b_bytes;
   return w;
 }
 
 size_t build_tc_workspace_bytes(int B, int C, int H, int W, int mode) { return ws_layout(B, C, H, W, mode).total; }
 
-int launch_build_tc(const float* f1, const float* f2, void* const* pyr, const rcb_pyramid_layout& lay, int B,
-                    int C, int H, int W, int mode, void* ws, size_t ws_bytes, cudaStream_t s) {
+// MMA schedule of a tile = the order of the boxes in a tile image; fills p.box / p.nbox and the pack's box tables
+static void make_schedule(const WsLayout& wl, int mode, tc::Params& p, tc::PackParams& pk) {
+  using namespace tc;
+  for (int i = 0; i < 4; ++i) pk.box16_hi[i] = pk.box16_lo[i] = -1;
+  for (int i = 0; i < 2; ++i) pk.box8_hi[i] = pk.box8_lo[i] = -1;
+  int n = 0;
+  const int nk16 = wl.K16 / 64;
+  if (mode == RCB_BUILD_F16F8) {
+    const int col_hi8 = wl.K16 / 2, col_lo8 = col_hi8 + wl.K8 / 4;
+    for (int k8 = 0; k8 < wl.K8 / 128; ++k8) {  // cross terms first, accumulated at a scale of 2^12
+      pk.box8_hi[k8] = n;
+      p.box[n++] = BoxDesc{col_lo8 + k8 * 32, -1, KIND_F8, make_idesc(0), 0};  // e4m3(B_hi) x A_lo
+      pk.box8_lo[k8] = n;
+      p.box[n++] = BoxDesc{col_hi8 + k8 * 32, -1, KIND_F8, make_idesc(0), 0};  // B_lo x e4m3(A_hi)
+    }
+    for (int kb = 0; kb < nk16; ++kb) {
+      pk.box16_hi[kb] = n;
+      p.box[n++] = BoxDesc{kb * 32, -1, KIND_F16, make_idesc(0), kb == 0 ? 1 : 0};
+    }
+  } else if (mode == RCB_BUILD_BF16X3) {
+    for (int kb = 0; kb < nk16; ++kb) {
+      pk.box16_hi[kb] = n;
+      p.box[n++] = BoxDesc{kb * 32, wl.K16 / 2 + kb * 32, KIND_F16, make_idesc(1), 0};
+      pk.box16_lo[kb] = n;
+      p.box[n++] = BoxDesc{kb * 32, -1, KIND_F16, make_idesc(1), 0};
+    }
+  } else {
+    for (int kb = 0; kb < nk16; ++kb) {
+      pk.box16_hi[kb] = n;
+      p.box[n++] = BoxDesc{kb * 32, -1, KIND_F16, make_idesc(1), 0};
+    }
+  }
+  p.nbox = n;
+}
+
+static int check_ws(const WsLayout& wl, const void* ws, size_t ws_bytes) {
+  if (wl.a_words > 256 || wl.nbox > tc::MAX_BOX) return RCB_ERR_UNSUPPORTED;  // A stays resident in tensor memory (C <= 256)
+  if (!ws || ws_bytes < wl.total || (reinterpret_cast<uintptr_t>(ws) & 127)) return RCB_ERR_WORKSPACE;
+  return RCB_OK;
+}
+
+// pack: fp32 NCHW -> A image (queries) and B tile images (targets) in `ws`
+int launch_pack_tc(const float* f1, const float* f2, int B, int C, int H, int W, int mode, void* ws, size_t ws_bytes,
+                   cudaStream_t s) {
+  using namespace tc;
+  const WsLayout wl = ws_layout(B, C, H, W, mode);
+  int st = check_ws(wl, ws, ws_bytes);
+  if (st != RCB_OK) return st;
+  Params p{};
+  PackParams pk{};
+  make_schedule(wl, mode, p, pk);
+  const bool f8 = mode == RCB_BUILD_F16F8;
+  pk.a_img = static_cast<unsigned char*>(ws);
+  pk.a_row = (long long)wl.a_words * 4;
+  pk.a_lo16 = mode == RCB_BUILD_BF16X3 ? wl.K16 * 2 : -1;
+  pk.a_hi8 = wl.K16 * 2;
+  pk.a_lo8 = wl.K16 * 2 + wl.K8;
+  pk.b_img = pk.a_img + wl.a_bytes;
+  pk.nbox = p.nbox;
+  pk.pcols = wl.pcols;
+  pk.npatch = wl.pcols * wl.prows;
+  pk.Hp = wl.prows * PH;
+  pk.Wp = wl.pcols * PW;
+  pk.K16 = wl.K16;
+  pk.K8 = wl.K8;
+  dim3 grid((pk.Hp * pk.Wp + 63) / 64, (f8 ? wl.K8 : wl.K16) / 64, 2 * B);
+  if (f8) pack_operands_kernel<true><<<grid, 256, 0, s>>>(f1, f2, pk, B, C, H, W);
+  else pack_operands_kernel<false><<<grid, 256, 0, s>>>(f1, f2, pk, B, C, H, W);
+  return launch_status();
+}
+
+// main kernel on operands packed by launch_pack_tc (same B, C, H, W, mode)
+int launch_build_tc_packed(const void* ws, size_t ws_bytes, void* const* pyr, const rcb_pyramid_layout& lay, int B,
+                           int C, int H, int W, int mode, cudaStream_t s) {
   using namespace tc;
   const bool f16 = lay.dtype == RCB_F16;
   const int esize = f16 ? 2 : 4;
   const WsLayout wl = ws_layout(B, C, H, W, mode);
-  if (wl.a_words > 256) return RCB_ERR_UNSUPPORTED;  // A must stay resident in tensor memory (C <= 256)
+  int st = check_ws(wl, ws, ws_bytes);
+  if (st != RCB_OK) return st;
   if (!encode_fn()) return RCB_ERR_NO_DEVICE;
-  if (!ws || ws_bytes < wl.total || (reinterpret_cast<uintptr_t>(ws) & 127)) return RCB_ERR_WORKSPACE;
   const int Q = H * W;
-  const bool f8 = mode == RCB_BUILD_F16F8;
-
-  // 1. pack: fp32 NCHW -> K-major tensor-core operands
-  unsigned char* a_img = static_cast<unsigned char*>(ws);
-  unsigned char* b16 = a_img + wl.a_bytes;
-  unsigned char* b8 = b16 + wl.b16_bytes;
+  const unsigned char* a_img = static_cast<const unsigned char*>(ws);
+  const unsigned char* b_img = a_img + wl.a_bytes;
+  Params p{};
   {
-    PackDst da{}, db{};
-    da.K16 = db.K16 = wl.K16;
-    da.K8 = db.K8 = wl.K8;
-    // A: one row of a_words words per query = [hi16 | lo16] (bf16x3) or [hi16 | hi8 | lo8] (f16f8)
-    da.p16 = a_img; da.row16 = (long long)wl.a_words * 4; da.batch16 = (long long)Q * da.row16;
-    da.lo16_off = mode == RCB_BUILD_BF16X3 ? (long long)wl.K16 * 2 : -1;
-    da.p8 = f8 ? a_img + wl.K16 * 2 : nullptr; da.row8 = da.row16; da.batch8 = da.batch16; da.lo8_off = wl.K8;
-    // B: [part][B][Q][K] tensors
-    db.p16 = b16; db.row16 = (long long)wl.K16 * 2; db.batch16 = (long long)Q * db.row16;
-    db.lo16_off = mode == RCB_BUILD_BF16X3 ? (long long)B * db.batch16 : -1;
-    db.p8 = f8 ? b8 : nullptr; db.row8 = wl.K8; db.batch8 = (long long)Q * db.row8; db.lo8_off = (long long)B * db.batch8;
-    dim3 grid((Q + 63) / 64, (f8 ? wl.K8 : wl.K16) / 64, 2 * B);
-    if (f8) pack_operands_kernel<true><<<grid, 256, 0, s>>>(f1, f2, da, db, B, C, Q);
-    else pack_operands_kernel<false><<<grid, 256, 0, s>>>(f1, f2, da, db, B, C, Q);
-    int st = launch_status();
-    if (st != RCB_OK) return st;
+    PackParams pk{};
+    make_schedule(wl, mode, p, pk);
   }
 
-  // 2. tensor maps
-  CUtensorMap map_b16, map_b8, map_l0, map_l1;
-  {
-    cuuint64_t dims[4] = {(cuuint64_t)wl.K16, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)wl.parts16 * B};
-    cuuint64_t str[3] = {(cuuint64_t)wl.K16 * 2, (cuuint64_t)W * wl.K16 * 2, (cuuint64_t)Q * wl.K16 * 2};
-    cuuint32_t box[4] = {64, PW, PH, 1};
-    if (!encode(&map_b16, f8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, b16, dims, str,
-                box, CU_TENSOR_MAP_SWIZZLE_128B))
-      return RCB_ERR_INVALID_ARGUMENT;
-  }
-  if (f8) {
-    cuuint64_t dims[4] = {(cuuint64_t)wl.K8, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)2 * B};
-    cuuint64_t str[3] = {(cuuint64_t)wl.K8, (cuuint64_t)W * wl.K8, (cuuint64_t)Q * wl.K8};
-    cuuint32_t box[4] = {128, PW, PH, 1};
-    if (!encode(&map_b8, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, b8, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B))
-      return RCB_ERR_INVALID_ARGUMENT;
-  } else {
-    map_b8 = map_b16;
-  }
+  CUtensorMap map_l0, map_l1;
   // stores: a level is viewed as [B][Q][tile rows][tiles_x * 16 words]; one box = 128 B (two fp32 tiles) x 32 queries
   for (int l = 0; l < 2; ++l) {
     CUtensorMap* m = l == 0 ? &map_l0 : &map_l1;
@@ -796,32 +915,7 @@ int launch_build_tc(const float* f1, const float* f2, void* const* pyr, const rc
       return RCB_ERR_INVALID_ARGUMENT;
   }
 
-  // 3. MMA schedule of a tile
-  Params p{};
-  {
-    int n = 0;
-    const int nk16 = wl.K16 / 64;
-    if (f8) {
-      const int col_hi8 = wl.K16 / 2, col_lo8 = col_hi8 + wl.K8 / 4;
-      for (int k8 = 0; k8 < wl.K8 / 128; ++k8) {  // cross terms first, accumulated at a scale of 2^12
-        p.box[n++] = BoxDesc{1, 0, k8 * 128, col_lo8 + k8 * 32, -1, KIND_F8, make_idesc(0), 0};  // e4m3(B_hi) x A_lo
-        p.box[n++] = BoxDesc{1, 1, k8 * 128, col_hi8 + k8 * 32, -1, KIND_F8, make_idesc(0), 0};  // B_lo x e4m3(A_hi)
-      }
-      for (int kb = 0; kb < nk16; ++kb)
-        p.box[n++] = BoxDesc{0, 0, kb * 64, kb * 32, -1, KIND_F16, make_idesc(0), kb == 0 ? 1 : 0};
-    } else if (mode == RCB_BUILD_BF16X3) {
-      for (int kb = 0; kb < nk16; ++kb) {
-        p.box[n++] = BoxDesc{0, 0, kb * 64, kb * 32, wl.K16 / 2 + kb * 32, KIND_F16, make_idesc(1), 0};
-        p.box[n++] = BoxDesc{0, 1, kb * 64, kb * 32, -1, KIND_F16, make_idesc(1), 0};
-      }
-    } else {
-      for (int kb = 0; kb < nk16; ++kb) p.box[n++] = BoxDesc{0, 0, kb * 64, kb * 32, -1, KIND_F16, make_idesc(1), 0};
-    }
-    if (n > MAX_BOX) return RCB_ERR_UNSUPPORTED;
-    p.nbox = n;
-  }
-
-  // 4. work decomposition
+  // work decomposition
   p.B = B; p.C = C; p.H = H; p.W = W; p.Q = Q;
   p.levels = lay.levels;
   p.mtiles = (Q + BM - 1) / BM;
@@ -836,6 +930,7 @@ int launch_build_tc(const float* f1, const float* f2, void* const* pyr, const rc
   p.f16 = f16 ? 1 : 0;
   p.a_words = wl.a_words;
   p.a_pack = reinterpret_cast<const uint32_t*>(a_img);
+  p.b_img = b_img;
   p.acc_col0 = (wl.a_words + 127) / 128 * 128;  // A occupies the first a_words TMEM columns
   p.nacc = (512 - p.acc_col0) / BN < MAX_ACC ? (512 - p.acc_col0) / BN : MAX_ACC;
 #ifdef RCB_DEBUG
@@ -843,8 +938,8 @@ int launch_build_tc(const float* f1, const float* f2, void* const* pyr, const rc
   p.debug_skip = debug_env_int("RCB_TC_DEBUG_SKIP", 0);
 #endif
 
-  const int stg_total = NUM_EPI_WARPS * STG0_BYTES + 4 * STG1_BYTES;
-  int nstage = (SMEM_BUDGET - BAR_BYTES - stg_total) / STAGE_BYTES;
+  const int stg_total = NUM_EPI_WARPS * STG0_BYTES + 4 * STG1_BYTES + 4 * XCH_BYTES;
+  int nstage = (SMEM_BUDGET - BAR_BYTES - stg_total) / STAGE_BYTES;  // 9 boxes of 16 KB
   if (nstage > MAX_STAGE) nstage = MAX_STAGE;
   {
     const int ns = debug_env_int("RCB_TC_NSTAGE", nstage);
@@ -855,7 +950,8 @@ int launch_build_tc(const float* f1, const float* f2, void* const* pyr, const rc
   p.b_off = 0;
   p.stg0_off = p.b_off + nstage * STAGE_BYTES;
   p.stg1_off = p.stg0_off + NUM_EPI_WARPS * STG0_BYTES;
-  p.bar_off = p.stg1_off + 4 * STG1_BYTES;
+  p.xch_off = p.stg1_off + 4 * STG1_BYTES;
+  p.bar_off = p.xch_off + 4 * XCH_BYTES;
   const int smem_total = p.bar_off + BAR_BYTES;
 
   // one CTA per SM.  Units (batch, query tile) go round-robin over the CTAs; what is left after the full rounds is
@@ -865,16 +961,26 @@ int launch_build_tc(const float* f1, const float* f2, void* const* pyr, const rc
   if (ctas > units * p.npatch) ctas = units * p.npatch;
   p.full_rounds = units / ctas;
   const int left = units % ctas;
+  // (pieces are whole patch rows -- row PAIRS in the paired sweep order: the level-3 epilogue pairs horizontally
+  // adjacent patches and level-2 lines are completed by 2 x 2 patches)
+  const int rows_per = RCB_PAIR_ORDER ? 2 : 1, rgroups = (p.prows + rows_per - 1) / rows_per;
   p.tail_split = left ? ctas / left : 1;
-  if (p.tail_split > p.npatch) p.tail_split = p.npatch;
-  p.tail_len = (p.npatch + p.tail_split - 1) / p.tail_split;
+  if (p.tail_split > rgroups) p.tail_split = rgroups;
+  p.tail_len = (rgroups + p.tail_split - 1) / p.tail_split * rows_per * p.pcols;
   p.tail_split = (p.npatch + p.tail_len - 1) / p.tail_len;
   p.tail_pieces = left * p.tail_split;
 
   cudaError_t e = cudaFuncSetAttribute(build_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET);
   if (e != cudaSuccess) return (int)e;
-  build_tc_kernel<<<ctas, THREADS, smem_total, s>>>(map_b16, map_b8, map_l0, map_l1, p);
+  build_tc_kernel<<<ctas, THREADS, smem_total, s>>>(map_l0, map_l1, p);
   return launch_status();
+}
+
+int launch_build_tc(const float* f1, const float* f2, void* const* pyr, const rcb_pyramid_layout& lay, int B,
+                    int C, int H, int W, int mode, void* ws, size_t ws_bytes, cudaStream_t s) {
+  const int st = launch_pack_tc(f1, f2, B, C, H, W, mode, ws, ws_bytes, s);
+  if (st != RCB_OK) return st;
+  return launch_build_tc_packed(ws, ws_bytes, pyr, lay, B, C, H, W, mode, s);
 }
 
 }  // namespace rcb

@@ -130,6 +130,10 @@ int launch_pool_levels(void* const* pyr, const rcb_pyramid_layout& lay, int B, i
 size_t build_tc_workspace_bytes(int B, int C, int H, int W, int mode);
 int launch_build_tc(const float* f1, const float* f2, void* const* pyr, const rcb_pyramid_layout& lay, int B,
                     int C, int H, int W, int mode, void* ws, size_t ws_bytes, cudaStream_t s);
+int launch_pack_tc(const float* f1, const float* f2, int B, int C, int H, int W, int mode, void* ws, size_t ws_bytes,
+                   cudaStream_t s);
+int launch_build_tc_packed(const void* ws, size_t ws_bytes, void* const* pyr, const rcb_pyramid_layout& lay, int B,
+                           int C, int H, int W, int mode, cudaStream_t s);
 int launch_lookup(const void* const* pyr, const rcb_pyramid_layout& lay, const float* coords, float* out, int B,
                   int H, int W, int radius, cudaStream_t s);
 size_t lookup_plan_bytes();

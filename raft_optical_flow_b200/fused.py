@@ -5,6 +5,9 @@ block, ``cor = F.relu(self.convc1(corr))`` (core/update.py:154 SmallMotionEncode
 ``LazyCorrBlock`` defers the lookup: its call returns a handle, and the patched encoder ``forward`` resolves the handle
 with one ``CorrBlock.lookup_conv`` launch, so the correlation tensor never exists.  Inference only -- whenever autograd
 is recording, the handle is never created and the reference's own two steps run on the materialised tensor.
+Accuracy class: the fused layer feeds fp16 operands to the tensor cores (~3e-4 of max-abs against an fp32 convolution,
+the class of the TF32 convolution cuDNN runs for the reference by default); ``patch_raft(fuse_motion_encoder=True)``
+enables it for ALL no-grad inference of the patched model.
 """
 import sys
 
@@ -34,14 +37,25 @@ class LazyCorrBlock(CorrBlock):
         return _LazyCorr(self, coords)
 
 
+_PACKED = {}      # (device, weight ptr, weight version, bias ptr, bias version, dtype, levels, radius) -> PackedConvC1
+_PACKED_MAX = 32  # a handful of models x devices; oldest entries are dropped
+
+
 def _packed_for(conv, block):
-    w = conv.weight
-    key = (w.data_ptr(), w._version, None if conv.bias is None else conv.bias._version, block.num_levels, block.radius)
-    cached = getattr(conv, "_rcb_packed", None)
-    if cached is None or cached[0] != key:
-        cached = (key, PackedConvC1(w, conv.bias, block.num_levels, block.radius))
-        conv._rcb_packed = cached
-    return cached[1]
+    """Packed convc1 weights, cached at MODULE level and keyed by the parameter storage itself: nn.DataParallel
+    (the reference's demo.py / evaluate.py) rebuilds its replicas on every forward, so a cache hung on the conv module
+    would never hit and the weights would be re-packed on every GRU iteration; replicas of one device share the
+    broadcast parameter memory only within a forward, so the key also carries the version counters."""
+    w, b = conv.weight, conv.bias
+    key = (w.device, w.data_ptr(), w._version, None if b is None else b.data_ptr(), None if b is None else b._version,
+           w.dtype, block.num_levels, block.radius)
+    packed = _PACKED.get(key)
+    if packed is None:
+        packed = PackedConvC1(w, b, block.num_levels, block.radius)
+        if len(_PACKED) >= _PACKED_MAX:
+            _PACKED.pop(next(iter(_PACKED)))
+        _PACKED[key] = packed
+    return packed
 
 
 def _supported(conv):

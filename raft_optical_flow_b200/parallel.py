@@ -158,11 +158,13 @@ class GradBucketReducer:
 
     Parameters are grouped into fixed buckets of ~bucket_bytes in REVERSE registration order (the order backward
     produces gradients in), one dtype per bucket, identical on every rank.  A post-accumulate-grad hook on every
-    parameter counts the bucket down; when a bucket is complete its gradients are flattened and an asynchronous
-    all_reduce is launched at once (NCCL: on the communicator's own stream, so it runs under the rest of backward;
-    gloo in the CPU tests), while autograd keeps producing the earlier layers' gradients.  ``finish()`` -- called
-    after ``loss.backward()`` -- flushes buckets some of whose parameters got no gradient this step (zeros stand in),
-    waits for the handles and scatters the averaged values back into ``.grad``.
+    parameter counts the bucket down; when a bucket is complete -- and every bucket before it has been launched, so
+    that all ranks issue their collectives in the same order even when a rank's graph skips a layer -- its gradients
+    are flattened and an asynchronous all_reduce is launched at once (NCCL: on the communicator's own stream, so it
+    runs under the rest of backward; gloo in the CPU tests), while autograd keeps producing the earlier layers'
+    gradients.  ``finish()`` -- called after ``loss.backward()`` -- launches what is left in order (zeros stand in for
+    a parameter that got no gradient this step), waits for the handles and scatters the averaged values back into
+    ``.grad``.
     """
 
     def __init__(self, params, bucket_bytes=4 << 20, average=True):
@@ -191,6 +193,7 @@ class GradBucketReducer:
         self._pending = [len(b) for b in self.buckets]
         self._ready = [set() for _ in self.buckets]
         self._inflight = {}
+        self._next = 0  # buckets [0, _next) have been launched
 
     def _on_grad(self, p):
         i = self._bucket_of[id(p)]
@@ -198,8 +201,8 @@ class GradBucketReducer:
             return  # a second accumulation into the same .grad within one step (not expected in RAFT)
         self._ready[i].add(id(p))
         self._pending[i] -= 1
-        if self._pending[i] == 0:
-            self._launch(i)
+        while self._next < len(self.buckets) and self._pending[self._next] == 0:
+            self._launch(self._next)
 
     def _launch(self, i):
         grads = []
@@ -211,14 +214,14 @@ class GradBucketReducer:
         handle = dist.all_reduce(flat, op=dist.ReduceOp.SUM, async_op=True)
         self._inflight[i] = (flat, handle, grads)
         self.launch_order.append(i)
+        self._next = i + 1
 
     def finish(self):
         """Call after backward.  Returns the number of all-reduce launches of this step."""
         if not self.enabled:
             return 0
-        for i in range(len(self.buckets)):
-            if i not in self._inflight:  # some parameter of the bucket received no gradient on this rank
-                self._launch(i)
+        for i in range(self._next, len(self.buckets)):  # a parameter of bucket _next received no gradient on this rank
+            self._launch(i)
         world = dist.get_world_size()
         for i, (flat, handle, grads) in self._inflight.items():
             handle.wait()

@@ -52,12 +52,54 @@ def upsample_flow(flow, mask):
     return _UpsampleFn.apply(flow, mask)
 
 
-def patch_raft(raft_module, fuse_motion_encoder=False):
+class _GraphedInference:
+    """RAFT.forward(test_mode=True) under no_grad as ONE CUDA graph per (model, input shape, iters): the reference's
+    GRU loop (core/raft.py:214-243) issues ~150 small kernels per iteration from Python, and at batch 1 the host
+    cannot feed the GPU -- the lookup then runs at a quarter of its roofline behind launch latency.  The first call
+    with a new key runs the model eagerly twice (cuDNN autotuning, allocator warm-up) and captures the third run;
+    later calls copy the frames into the graph's input buffers, replay, and return copies of the outputs.  Every
+    kernel of this package is capture-safe (no allocation, no synchronisation, plans are host-side data)."""
+
+    def __init__(self, original):
+        self.original = original
+        self.cache = {}
+
+    def __call__(self, module, image1, image2, iters=12, flow_init=None, upsample=True, test_mode=False):
+        if (not test_mode or torch.is_grad_enabled() or flow_init is not None or not image1.is_cuda
+                or torch.cuda.is_current_stream_capturing()):
+            return self.original(module, image1, image2, iters=iters, flow_init=flow_init, upsample=upsample,
+                                 test_mode=test_mode)
+        key = (id(module), tuple(image1.shape), image1.dtype, image1.device, int(iters), module.training)
+        entry = self.cache.get(key)
+        if entry is None:
+            in1, in2 = image1.clone(), image2.clone()
+            side = torch.cuda.Stream(image1.device)
+            side.wait_stream(torch.cuda.current_stream(image1.device))
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    self.original(module, in1, in2, iters=iters, test_mode=True)
+            torch.cuda.current_stream(image1.device).wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = self.original(module, in1, in2, iters=iters, test_mode=True)
+            entry = (graph, in1, in2, out)
+            self.cache[key] = entry
+        graph, in1, in2, out = entry
+        in1.copy_(image1)
+        in2.copy_(image2)
+        graph.replay()
+        return tuple(o.clone() for o in out)
+
+
+def patch_raft(raft_module, fuse_motion_encoder=False, cuda_graph=False):
     """Installs CorrBlock / AlternateCorrBlock at the module globals core/raft.py:187,189 looks up and the fused
     convex upsampling as RAFT.upsample_flow (core/raft.py:112,240).  Returns the replaced objects.
     fuse_motion_encoder=True additionally defers every lookup into the motion encoder's first layer (fused.py:
     one kernel for corr_fn(coords1) + relu(convc1(.)), inference only); undo that part with the function stored as
-    ``raft_module._rcb_undo_fused``."""
+    ``raft_module._rcb_undo_fused``.
+    cuda_graph=True additionally replays no-grad ``test_mode`` forwards as one CUDA graph per input shape
+    (``_GraphedInference``; the parameters are read in place, so weight updates are seen; undo with
+    ``raft_module._rcb_undo_graph()``)."""
     from .corr import AlternateCorrBlock, CorrBlock
     old = (raft_module.CorrBlock, raft_module.AlternateCorrBlock, raft_module.RAFT.upsample_flow)
     raft_module.CorrBlock, raft_module.AlternateCorrBlock = CorrBlock, AlternateCorrBlock
@@ -65,4 +107,17 @@ def patch_raft(raft_module, fuse_motion_encoder=False):
     if fuse_motion_encoder:
         from .fused import install_fused_motion_encoder
         raft_module._rcb_undo_fused = install_fused_motion_encoder(raft_module)
+    if cuda_graph:
+        original = raft_module.RAFT.forward
+        graphed = _GraphedInference(original)
+
+        def forward(self, image1, image2, iters=12, flow_init=None, upsample=True, test_mode=False):
+            return graphed(self, image1, image2, iters=iters, flow_init=flow_init, upsample=upsample, test_mode=test_mode)
+
+        raft_module.RAFT.forward = forward
+
+        def undo():
+            raft_module.RAFT.forward = original
+            graphed.cache.clear()
+        raft_module._rcb_undo_graph = undo
     return old

@@ -237,12 +237,35 @@ def case_motion_encoder_convc1():
              weight=enc.convc1.weight.detach().numpy(), bias=enc.convc1.bias.detach().numpy(), cor=cor.numpy())
 
 
+def case_sequence_loss():
+    """Training harness row (scope table 8f, f4): the reference's sequence_loss (train.py:47-106).  train.py itself cannot
+    be imported here (matplotlib / tensorboard / datasets at module level), so the function definition is lifted out of
+    the file's syntax tree and executed unchanged; stores loss, metrics and d loss / d predictions."""
+    import ast
+    src = open(os.path.join(REF, "train.py")).read()
+    fn = next(n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == "sequence_loss")
+    ns = {"torch": torch, "MAX_FLOW": 400}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), "train.py", "exec"), ns)
+    g = rs(901)
+    N, H, W, n = 2, 12, 20, 5
+    gt = (30.0 * g.standard_normal((N, 2, H, W))).astype(np.float32)
+    gt[0, :, 3, 4] = 500.0  # beyond MAX_FLOW: excluded
+    preds = [(gt + (4.0 / (i + 1)) * g.standard_normal((N, 2, H, W))).astype(np.float32) for i in range(n)]
+    valid = (g.uniform(size=(N, H, W)) > 0.2).astype(np.float32)
+    tp = [torch.from_numpy(p).clone().requires_grad_(True) for p in preds]
+    loss, metrics = ns["sequence_loss"](tp, torch.from_numpy(gt), torch.from_numpy(valid), gamma=0.8)
+    loss.backward()
+    save("sequence_loss", meta=np.array([N, H, W, n]), flow_gt=gt, valid=valid, preds=np.stack(preds),
+         loss=np.float32(loss.item()), metrics=np.array([metrics[k] for k in ("epe", "1px", "3px", "5px")], np.float32),
+         dpreds=np.stack([t.grad.numpy() for t in tp]))
+
+
 if __name__ == "__main__":
     p = argparse.ArgumentParser()
     p.add_argument("--only", default=None)
     a = p.parse_args()
     cases = [case_odd, case_full, case_small, case_edges, case_known_answers, case_alt_formulation,
-             case_raft_small_crop, case_upsample_flow, case_motion_encoder_convc1]
+             case_raft_small_crop, case_upsample_flow, case_motion_encoder_convc1, case_sequence_loss]
     for c in cases:
         if a.only is None or a.only in c.__name__:
             c()

@@ -220,3 +220,32 @@ def test_training_step_gradients_match_reference(ref):
     print(f"loss ref {l_ref:.6f} ours {l_our:.6f}; fnet grad relative L2 error {rel:.2e}")
     assert abs(l_our - l_ref) <= 1e-3 * abs(l_ref)
     assert rel <= 2e-3  # TF32 is off in both arms; what remains is fp32 summation order (atomics in the backward kernels)
+
+
+def test_cuda_graph_inference_matches_eager(ref):
+    """patch_raft(cuda_graph=True): no-grad test_mode forwards replayed as one CUDA graph per input shape give the
+    same flow as the eager patched model, for new frames too (inputs are copied into the graph's buffers), and leave
+    training-mode / autograd calls on the eager path."""
+    import raft_optical_flow_b200 as rcb
+    d, raft_mod, ref_corr, InputPadder = ref
+    model, i1, i2 = _load(d, raft_mod, InputPadder, alternate=False)
+    a1, a2 = i1[:, :, :192, :256].contiguous(), i2[:, :, :192, :256].contiguous()
+    b1, b2 = i1[:, :, 100:292, 300:556].contiguous(), i2[:, :, 100:292, 300:556].contiguous()
+    old = rcb.patch_raft(raft_mod)
+    try:
+        want_a, want_b = _flow(model, a1, a2, 6), _flow(model, b1, b2, 6)
+    finally:
+        raft_mod.CorrBlock, raft_mod.AlternateCorrBlock, raft_mod.RAFT.upsample_flow = old
+    old = rcb.patch_raft(raft_mod, cuda_graph=True)
+    try:
+        got_a = _flow(model, a1, a2, 6)          # warm-up + capture
+        got_b = _flow(model, b1, b2, 6)          # replay on new frames
+        got_a2 = _flow(model, a1, a2, 6)         # replay again
+        for got, want in ((got_a, want_a), (got_b, want_b), (got_a2, want_a)):
+            assert _epe(got, want)[1] <= 1e-3
+        assert want_a.abs().max().item() > 1.0 and _epe(want_a, want_b)[0] > 0.1  # the two inputs really differ
+        preds = model(a1, a2, iters=2)            # autograd on: eager path, differentiable
+        assert len(preds) == 2 and preds[-1].requires_grad
+    finally:
+        raft_mod._rcb_undo_graph()
+        raft_mod.CorrBlock, raft_mod.AlternateCorrBlock, raft_mod.RAFT.upsample_flow = old

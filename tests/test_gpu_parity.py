@@ -703,3 +703,78 @@ def test_lookup_sweep_of_small_geometries_vs_oracle(rcb, dev, orc, seed):
         got = blk(t(coords, dev)).cpu().numpy()
         assert np.isfinite(got).all()
         assert rel_err(got, want) < tol, (seed, pdt, B, C, H, W, r, L)
+
+
+# ---------------------------------------------------------------------------------------------
+# scope table 8f, f2: operands packed once from the encoder's [2N, C, H, W] output
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mode", [m for m in PARITY_MODES if m != "fp32"] + ["bf16"])
+@pytest.mark.parametrize("shape", [(2, 64, 23, 39, 4, 4), (1, 128, 30, 44, 4, 3), (1, 200, 17, 21, 3, 4)])
+def test_from_packed_equals_unpacked_and_oracle(rcb, dev, orc, shape, mode):
+    """CorrBlock.from_packed(PackedFmaps(fnet output)) == CorrBlock(fmap1, fmap2) bit for bit (the same two kernels,
+    launched through rcb_corr_pack_fmaps + rcb_corr_build_packed), and both match the oracle."""
+    B, C, H, W, L, r = shape
+    f1, f2, coords = seeded(300 + H, B, C, H, W)
+    fmaps = t(np.concatenate([f1, f2], 0), dev)  # what fnet([image1, image2]) holds before torch.split
+    packed = rcb.PackedFmaps(fmaps, mode=mode)
+    a = rcb.CorrBlock.from_packed(packed, num_levels=L, radius=r)
+    b = rcb.CorrBlock(fmaps[:B], fmaps[B:], num_levels=L, radius=r, mode=mode)
+    for la, lb in zip(a.corr_pyramid, b.corr_pyramid):
+        assert torch.equal(la, lb)
+    out = a(t(coords, dev))
+    assert torch.equal(out, b(t(coords, dev)))
+    if mode != "bf16":
+        assert rel_err(out.cpu().numpy(), orc.OracleCorrBlock(f1, f2, L, r)(coords)) < TOL
+    with pytest.raises(RuntimeError):
+        rcb.PackedFmaps(fmaps, mode="fp32")
+
+
+# ---------------------------------------------------------------------------------------------
+# autograd through AlternateCorrBlock (the reference has none; gradients must equal CorrBlock's)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["corrblock_odd", "corrblock_full_r4"])
+def test_alternate_block_backward_golden(rcb, dev, name):
+    """d/d(fmap1, fmap2, coords) through AlternateCorrBlock against autograd through the REFERENCE CorrBlock (the two
+    formulations are equal by linearity, SURVEY 8c vi)."""
+    g = load_golden(name)
+    B, C, H, W, L, r, seed = [int(v) for v in g["meta"]]
+    f1 = t(g["fmap1"], dev).requires_grad_(True)
+    f2 = t(g["fmap2"], dev).requires_grad_(True)
+    co = t(g["coords"], dev).requires_grad_(True)
+    out = rcb.AlternateCorrBlock(f1, f2, num_levels=L, radius=r)(co)
+    assert rel_err(out.detach().cpu().numpy(), g["out"]) < TOL
+    out.backward(t(cotangent(seed, g["out"].shape), dev))
+    assert rel_err(f1.grad.cpu().numpy(), g["df1"]) < GRAD_TOL
+    assert rel_err(f2.grad.cpu().numpy(), g["df2"]) < GRAD_TOL
+    assert rel_err(co.grad.cpu().numpy(), g["dcoords"]) < GRAD_TOL
+
+
+def test_alternate_block_backward_accumulates_vs_oracle(rcb, dev, orc):
+    """Two calls of one block (two GRU iterations), odd sizes: gradients add up; checked against the oracle's
+    CorrBlock backward and, per level, against oracle.altcorr_backward(true_coords_grad=True)."""
+    B, C, H, W, L, r = 2, 24, 11, 13, 3, 3
+    f1n, f2n, c0 = seeded(61, B, C, H, W, sigma=2.0)
+    _, _, c1 = seeded(62, B, C, H, W, sigma=2.0)
+    f1 = t(f1n, dev).requires_grad_(True)
+    f2 = t(f2n, dev).requires_grad_(True)
+    co = t(c0, dev).requires_grad_(True)
+    blk = rcb.AlternateCorrBlock(f1, f2, num_levels=L, radius=r)
+    o0, o1 = blk(co), blk(t(c1, dev))
+    g0, g1 = cotangent(63, tuple(o0.shape)), cotangent(64, tuple(o1.shape))
+    (o0 * t(g0, dev)).sum().add((o1 * t(g1, dev)).sum()).backward()
+    ob = orc.OracleCorrBlock(f1n, f2n, L, r)
+    a1, a2, ac = ob.backward(c0, g0)
+    b1, b2, _ = ob.backward(c1, g1)
+    assert rel_err(f1.grad.cpu().numpy(), a1 + b1) < GRAD_TOL
+    assert rel_err(f2.grad.cpu().numpy(), a2 + b2) < GRAD_TOL
+    assert rel_err(co.grad.cpu().numpy(), ac) < GRAD_TOL
+    # level 0 of the first call through the extension-level oracle
+    rd2 = (2 * r + 1) ** 2
+    cg = (g0[:, :rd2] / np.sqrt(C)).reshape(B, 1, rd2, H, W)
+    _, _, wc = orc.altcorr_backward(f1n.transpose(0, 2, 3, 1), f2n.transpose(0, 2, 3, 1),
+                                    c0.transpose(0, 2, 3, 1).reshape(B, 1, H, W, 2), cg, r, true_coords_grad=True)
+    only0 = np.zeros_like(g0)
+    only0[:, :rd2] = g0[:, :rd2]
+    co2 = t(c0, dev).requires_grad_(True)
+    rcb.AlternateCorrBlock(t(f1n, dev), t(f2n, dev), num_levels=L, radius=r)(co2).backward(t(only0, dev))
+    assert rel_err(co2.grad.cpu().numpy(), wc.reshape(B, H, W, 2).transpose(0, 3, 1, 2)) < GRAD_TOL

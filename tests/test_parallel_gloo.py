@@ -3,6 +3,7 @@ gradient all-reduce that replaces nn.DataParallel's reduction (reference train.p
 import os
 import socket
 
+import numpy as np
 import pytest
 import torch
 import torch.distributed as dist
@@ -45,10 +46,48 @@ def _worker(rank, world, port, out):
     launches = parallel.allreduce_grads(params, bucket_bytes=64, average=True)
     span = parallel.shard_range(9, world, rank)
     reducer_result = _reducer_case(rank, world)
-    out.put((rank, tmax, launches, [p.grad.clone() if p.grad is not None else None for p in params], span,
-             reducer_result))
+    step_result = {ov: _train_step_case(rank, world, ov) for ov in (True, False)}
+    # numpy arrays travel through the queue by value (tensors would be shared by file descriptor and need this
+    # process to be alive when the parent unpickles them)
+    out.put((rank, tmax, launches, [p.grad.numpy().copy() if p.grad is not None else None for p in params], span,
+             reducer_result, step_result))
     dist.barrier()
     dist.destroy_process_group()
+
+
+class _ToyFlow(torch.nn.Module):
+    """Stands in for RAFT: `iters` predictions [N, 2, H, W]."""
+
+    def __init__(self):
+        super().__init__()
+        self.a = torch.nn.Conv2d(6, 8, 3, padding=1)
+        self.b = torch.nn.Conv2d(8, 2, 3, padding=1)
+
+    def forward(self, image1, image2, iters=3):
+        f = self.b(torch.tanh(self.a(torch.cat([image1, image2], 1) / 255.0)))
+        return [f * (i + 1) / iters for i in range(iters)]
+
+
+def _toy_batch(world):
+    g = torch.Generator().manual_seed(7)
+    n = 2 * world
+    return (255 * torch.rand(n, 3, 8, 10, generator=g), 255 * torch.rand(n, 3, 8, 10, generator=g),
+            torch.randn(n, 2, 8, 10, generator=g), torch.ones(n, 8, 10))
+
+
+def _train_step_case(rank, world, overlap):
+    """train.TrainStep on this rank's shard of a fixed global batch; returns the parameters after two steps."""
+    from raft_optical_flow_b200 import train
+    torch.manual_seed(3)
+    net = _ToyFlow()
+    b, e = parallel.shard_range(2 * world, world, rank)
+    batch = [t[b:e] for t in _toy_batch(world)]
+    step = train.TrainStep(net, num_steps=50, iters=3, overlap=overlap, bucket_bytes=512)
+    for _ in range(2):
+        loss, _ = step(*batch)
+    launches = step.allreduce_launches
+    step.close()
+    return [p.detach().numpy().copy() for p in net.parameters()], launches
 
 
 def _reducer_case(rank, world):
@@ -68,7 +107,7 @@ def _reducer_case(rank, world):
             h = m[3](m[2](h))
         return m[4](h).square().sum()
 
-    red = parallel.GradBucketReducer(net.parameters(), bucket_bytes=256, average=True)
+    red = parallel.GradBucketReducer(net.parameters(), bucket_bytes=200, average=True)  # one bucket per layer
     results = []
     for step in range(2):  # state must reset between steps
         net.zero_grad(set_to_none=True)
@@ -101,13 +140,25 @@ def test_two_rank_gloo_allreduce_and_timing():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    for rank, tmax, launches, grads, span, reducer in results:
+    # single-process step on the whole batch: what every rank must end up with (equal shards, mean losses)
+    from raft_optical_flow_b200 import train
+    torch.manual_seed(3)
+    whole = _ToyFlow()
+    ref_step = train.TrainStep(whole, num_steps=50, iters=3)
+    for _ in range(2):
+        ref_step(*_toy_batch(world))
+    for rank, tmax, launches, grads, span, reducer, steps in results:
+        for overlap in (True, False):
+            got, n_launch = steps[overlap]
+            assert n_launch >= 1
+            for a, b in zip(got, whole.parameters()):
+                assert np.allclose(a, b.detach().numpy(), atol=2e-6), (overlap, np.abs(a - b.detach().numpy()).max())
         assert tmax == [2.0, 5.0]
         assert launches == 2  # 15*4 + 7*4 >= 64 bytes -> first bucket; the two small tensors flush at the end
         for i in range(3):
-            assert torch.allclose(grads[i], torch.full_like(grads[i], 1.5 * (i + 1)))  # mean of 1x and 2x
+            assert np.allclose(grads[i], 1.5 * (i + 1))  # mean of 1x and 2x
         # a gradient that exists on one rank only is averaged against zeros, with identical bucket layouts on all ranks
-        assert torch.allclose(grads[3], torch.full_like(grads[3], 4.0))
+        assert np.allclose(grads[3], 4.0)
         for n, nbuckets, in_backward, err in reducer:
             assert nbuckets >= 3 and n == nbuckets       # every bucket reduced exactly once per step
             assert len(in_backward) >= 1                 # ... and at least the last layer's already during backward
