@@ -540,6 +540,15 @@ def run_ours(args, cfg):
         torch.cuda.empty_cache()
         frames_e2e = e2e_frames_timing(torch, dev, cfg, world, mx, barrier, args.steps)
 
+    # every rank's own figures (GPUs of one box differ by a few percent; the headline is the slowest rank)
+    per_rank = None
+    if world > 1:
+        mine = torch.tensor([med_ms, build_ms * 1e3, lookup_ms * 1e3, host_lookup_us], dtype=torch.float64, device=dev)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = [{"rank": i, "ms_per_step": round(float(t[0]), 4), "build_us": round(float(t[1]), 1),
+                     "lookup_us": round(float(t[2]), 2), "host_us_per_lookup_call": round(float(t[3]), 1)}
+                    for i, t in enumerate(allr)]
     med_ms, min_ms, e2e_ms = mx([med_ms, min_ms, e2e_ms])
     if rank != 0:
         if world > 1:
@@ -603,6 +612,8 @@ def run_ours(args, cfg):
                                   "tensor_frac_executed": executed * build_tflops / tc_peak,
                                   "traffic": ncu_traffic("build"), "us_per_launch": build_ms * 1e3,
                                   "algorithmic_bytes_per_launch": build_bytes, "algorithmic_flops": flops}
+    if per_rank:
+        line["per_rank"] = per_rank
     if fast:
         line["fast_mode"] = fast
     if fused:
