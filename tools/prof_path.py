@@ -12,7 +12,7 @@ from raft_optical_flow_b200 import AlternateCorrBlock, CorrBlock  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--config", default="cfg2")
-ap.add_argument("--mode", default="bf16x3")
+ap.add_argument("--mode", default="f16f8")
 ap.add_argument("--lookups", type=int, default=4)
 ap.add_argument("--builds", type=int, default=2)
 ap.add_argument("--alt", action="store_true")

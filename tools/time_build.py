@@ -10,7 +10,7 @@ from raft_optical_flow_b200 import _cabi  # noqa: E402
 from raft_optical_flow_b200.corr import _Pyramid  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--config", default="cfg2")
-ap.add_argument("--mode", default="bf16x3")
+ap.add_argument("--mode", default="f16f8")
 ap.add_argument("--reps", type=int, default=20)
 ap.add_argument("--between", default="none", choices=["none", "lookups", "fill", "sleep"],
                 help="what runs between the timed builds: nothing (tight loop), the step's lookups, a 512 MB fill, "
