@@ -219,7 +219,7 @@ def test_training_step_gradients_match_reference(ref):
     rel = ((g_our - g_ref).norm() / g_ref.norm()).item()
     print(f"loss ref {l_ref:.6f} ours {l_our:.6f}; fnet grad relative L2 error {rel:.2e}")
     assert abs(l_our - l_ref) <= 1e-3 * abs(l_ref)
-    assert rel <= 2e-3  # TF32 is off in both arms; what remains is fp32 summation order (atomics in the backward kernels)
+    assert rel <= 1e-4  # TF32 is off in both arms; what remains is fp32 summation order (measured 7e-6)
 
 
 def test_cuda_graph_inference_matches_eager(ref):
