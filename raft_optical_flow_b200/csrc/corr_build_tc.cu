@@ -2,25 +2,25 @@
 //
 // Replaces CorrBlock.corr (reference core/corr.py:96-127: matmul + / sqrt(C)) and the avg_pool2d loop of
 // CorrBlock.__init__ (core/corr.py:52-54).  See DESIGN.md "K1" for the roofline discussion: with an fp32 pyramid the
-// kernel is bound by its 2.2 GB of stores (the memory system takes ~5.5-5.9 TB/s of this pattern,
+// kernel is bound by its 2.2 GB of stores (the memory system takes 4.0-5.5 TB/s of this pattern,
 // tools/probe/tma_store_probe2.cu), so the design goal is to keep the tensor pipe and the epilogue BELOW that bound.
 //
 //   pack kernel   fp32 NCHW feature maps -> K-major tensor-core operands (a transpose + split), per build mode:
 //     RCB_BUILD_F16F8    x = hi + lo, hi = fp16(x).  hi*hi runs as ONE full-rate kind::f16 pass; the two cross terms
 //                        hi*lo + lo*hi only need ~4 significant bits (they are 2^-12 of the product), so they run in
-//                        8-bit e4m3 on kind::f8f6f4 at twice the rate: e4m3(hi) x e4m3(lo * 2^12).  The 2^12 is undone
-//                        for free by the first kind::f16 MMA of a tile, which scales the accumulator it adds to
-//                        (tcgen05.mma ... scale-input-d = 12).  2 pass-equivalents of tensor work instead of the 3 of
-//                        bf16x3, error ~1e-5 of max-abs (tools/split_precision_probe.py; bound 1e-4).
+//                        8-bit e4m3 on kind::f8f6f4 (K = 32 per instruction): e4m3(hi) x e4m3(lo * 2^12).  The 2^12 is
+//                        undone for free by the first kind::f16 MMA of a tile, which scales the accumulator it adds to
+//                        (tcgen05.mma ... scale-input-d = 12).  32 instead of 48 MMAs per tile (2 pass-equivalents of
+//                        tensor work instead of 3), error ~1e-5 of max-abs (tools/split_precision_probe.py; bound 1e-4).
 //     RCB_BUILD_BF16X3   bf16 hi/lo, hi*hi + hi*lo + lo*hi, three full-rate passes, error ~5e-6 of max-abs; no range
 //                        restriction (fp16 overflows beyond 65504).
 //     RCB_BUILD_BF16     hi parts only (fast mode, ~2.6e-3).
 //   main kernel   persistent, warp-specialised, 320 threads per CTA, one CTA per SM:
 //     warp 0      producer: B tiles (an 8 x 16 PATCH of target pixels x 128 bytes of K = a 16 KB box) stream through an
-//                 mbarrier ring, two boxes per stage.  The pack kernel writes the target operand as ready-made TILE
+//                 mbarrier ring, one box per stage.  The pack kernel writes the target operand as ready-made TILE
 //                 IMAGES -- per (batch, patch) the boxes of the tile's MMA schedule back to back, rows already in the
-//                 SWIZZLE_128B order the MMA descriptors expect, out-of-image targets as zeros -- so a stage is ONE
-//                 linear cp.async.bulk of 32 contiguous KB.  (Round 1 fetched each box as a 4-D tensor-map box of 128
+//                 SWIZZLE_128B order the MMA descriptors expect, out-of-image targets as zeros -- so a box is ONE
+//                 linear cp.async.bulk of 16 contiguous KB.  (Round 1 fetched each box as a 4-D tensor-map box of 128
 //                 rows x 128 B: the TMA unit then spends ~3.3 cycles per row, 1024 rows per tile, and the B stream
 //                 alone took 290 us of the kernel, profiles/r2b_build_anatomy_band_split.txt.)
 //     warp 1      MMA issuer: M = 128 queries x N = 128 targets per instruction, the A operand (queries) lives in
@@ -53,7 +53,7 @@
 //   what bounds it  the store path: this pattern (128-byte rows, one per query plane, 28 KB apart) is absorbed at
 //                 4.0-5.5 TB/s depending on the GPU of the pool (tools/probe/tma_store_probe2.cu; a plain fill reaches
 //                 7.3), the epilogue + stores alone take ~500 us at cfg2, and MMAs and B loads add 60-90 us of
-//                 interference on top (profiles/r2c..r2f).
+//                 interference on top (profiles/r2c..r2l; measured-and-rejected variants are listed in DESIGN.md).
 #include "rcb_common.cuh"
 #include "tcgen05_util.cuh"
 #include "tma_util.cuh"
