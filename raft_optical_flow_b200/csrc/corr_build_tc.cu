@@ -80,7 +80,11 @@ constexpr int MAX_STAGE = 12;    // B ring depth is chosen at launch from the sh
 constexpr int MAX_ACC = 4;       // TMEM accumulator buffers (128 columns each); count chosen at launch
 constexpr int MAX_BOX = 8;       // B boxes per tile (C <= 256)
 constexpr int NUM_EPI_WARPS = 8;
-constexpr int THREADS = 32 * (2 + NUM_EPI_WARPS);
+#ifndef RCB_NUM_ISSUERS
+#define RCB_NUM_ISSUERS 2        // MMA-issuing warps: tiles alternate between them (1: a single issuer)
+#endif
+constexpr int NUM_ISSUERS = RCB_NUM_ISSUERS;
+constexpr int THREADS = 32 * (1 + NUM_ISSUERS + NUM_EPI_WARPS);  // producer, issuer A, 8 epilogue warps, [issuer B]
 constexpr int STG0_BYTES = 8192;  // per epilogue warp: the band's two level-0 boxes
 constexpr int STG1_BYTES = 4096;  // per lane quarter: the level-1 box both warps of the pair fill
 constexpr int XCH_BYTES = 512;    // per lane quarter: band 0's level-2 row for its partner (16 bytes per query)
@@ -129,7 +133,7 @@ struct Params {
 #ifdef RCB_DEBUG
   unsigned long long* prof;  // per-CTA cycle counters (16 per CTA)
   int debug_skip;   // bitmask: 1 skip level-0 TMA stores, 2 skip the level-1 store, 4 skip level 2/3, 8 skip staging writes,
-                    // 16 skip B loads, 32 skip MMAs, 64 skip TMEM loads
+                    // 16 skip B loads, 32 skip MMAs, 64 skip TMEM loads, 128 skip the whole epilogue body
 #endif
 };
 
@@ -393,7 +397,7 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_l0, const __grid_constan
 
   if (threadIdx.x == 0) {
     mbar_init(a_full, NUM_EPI_WARPS);  // every epilogue warp loads a share of A
-    mbar_init(a_empty, 1);
+    mbar_init(a_empty, NUM_ISSUERS);  // every issuer commits once per unit
     for (int s = 0; s < NSTAGE; ++s) {
       mbar_init(b_full(s), 1);
       mbar_init(b_empty(s), 1);
@@ -477,48 +481,63 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_l0, const __grid_constan
       p.prof[blockIdx.x * 16 + 1] = w0;
     }
 #endif
-  } else if (warp == 1) {
-    // =============================== MMA issuer (whole warp runs the loop, one lane issues) ===
+  } else if (warp == 1 || warp >= 2 + NUM_EPI_WARPS) {
+    // =============================== MMA issuers (whole warp runs the loop, one lane issues) ===
+    // The issuing side costs ~200 cycles per box (barrier wait, tcgen05 fence, elect, commit) and ~500 per tile on top
+    // of ~60 cycles per MMA, and tcgen05.mma issue is effectively synchronous (the time of the loop is the SUM,
+    // profiles/r2s_mma_pipeline_only.txt), so with 4 MMAs per 16 KB box the tensor pipe idled 40 % of the time under
+    // ONE issuer.  Two issuer warps take alternate tiles (with two accumulators each owns one): the overhead of one
+    // overlaps the MMAs of the other.  Both follow the same global box sequence through the ring; a stage is freed
+    // and an accumulator published by the commit of the thread whose MMAs used it; the A operand is released to the
+    // next unit when BOTH have committed (a_empty counts NUM_ISSUERS).
+    const int me = warp == 1 ? 0 : 1;  // issuer index
     const uint64_t desc_base = make_smem_desc(0);  // everything but the start address
     int s = 0, buf = 0;
-    uint32_t ph = 0, aph = 0, nunit = 0;
+    uint32_t ph = 0, aph = 0, nunit = 0, gtile = 0;
     for (int si = 0; si < nseg; ++si, ++nunit) {
       const Segment sg = segment(si);
       mbar_wait_t(a_full, nunit & 1, pw2);
       tc_fence_after();
-      for (int pi = sg.p_begin; pi < sg.p_end; ++pi) {
+      for (int pi = sg.p_begin; pi < sg.p_end; ++pi, ++gtile) {
+        if ((int)(gtile % NUM_ISSUERS) != me) {
+          // The other issuer's tile: step over its accumulator and its boxes -- but OBSERVE every phase of the stage
+          // barriers on the way.  A parity wait is only unambiguous one phase ahead of the last phase the waiter has
+          // seen; stepping over a lap would let this warp take the completed lap before it for its own box.
+          for (int j = 0; j < p.nbox; ++j) {
+            mbar_wait(b_full(s), ph);
+            if (++s == NSTAGE) { s = 0; ph ^= 1; }
+          }
+          if (++buf == NACC) { buf = 0; aph ^= 1; }  // (NACC is a multiple of NUM_ISSUERS: its phases are never skipped)
+          continue;
+        }
         mbar_wait_t(acc_empty(buf), aph ^ 1, pw1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + p.acc_col0 + buf * BN;
         uint32_t acc = 0;
-        for (int j = 0; j < p.nbox; j += BOXES_PER_STAGE) {
+        for (int j = 0; j < p.nbox; ++j) {
           mbar_wait_t(b_full(s), ph, pw0);
           tc_fence_after();
           if (elect_one()) {
-            const int nbox = min(BOXES_PER_STAGE, p.nbox - j);
             if (!RCB_SKIP(p, 32)) {
-              for (int i = 0; i < nbox; ++i) {
-                const BoxDesc& bx = p.box[j + i];
-                const uint64_t bdesc =
-                    desc_base | (uint64_t)(((smem_base + p.b_off + s * STAGE_BYTES + i * BOX_BYTES) >> 4) & 0x3FFF);
-                const uint32_t ta0 = tmem_base + bx.a_col0;
-                if (bx.kind == KIND_F8) {
+              const BoxDesc& bx = p.box[j];
+              const uint64_t bdesc = desc_base | (uint64_t)(((smem_base + p.b_off + s * STAGE_BYTES) >> 4) & 0x3FFF);
+              const uint32_t ta0 = tmem_base + bx.a_col0;
+              if (bx.kind == KIND_F8) {
 #pragma unroll
-                  for (int k = 0; k < 4; ++k) {  // +32 bytes (smem) / +8 columns (TMEM) per K step
-                    umma_f8_ts(d_tmem, ta0 + 8 * k, bdesc + 2 * k, bx.idesc, acc);
-                    acc = 1;
-                  }
-                } else {
-                  if (bx.scaled) umma_f16_ts_scaled12(d_tmem, ta0, bdesc, bx.idesc);  // acc = 2^-12 acc + a * b
-                  else umma_f16_ts(d_tmem, ta0, bdesc, bx.idesc, acc);
+                for (int k = 0; k < 4; ++k) {  // +32 bytes (smem) / +8 columns (TMEM) per K step
+                  umma_f8_ts(d_tmem, ta0 + 8 * k, bdesc + 2 * k, bx.idesc, acc);
                   acc = 1;
+                }
+              } else {
+                if (bx.scaled) umma_f16_ts_scaled12(d_tmem, ta0, bdesc, bx.idesc);  // acc = 2^-12 acc + a * b
+                else umma_f16_ts(d_tmem, ta0, bdesc, bx.idesc, acc);
+                acc = 1;
 #pragma unroll
-                  for (int k = 1; k < 4; ++k) umma_f16_ts(d_tmem, ta0 + 8 * k, bdesc + 2 * k, bx.idesc, 1u);
-                  if (bx.a_col1 >= 0) {  // bf16x3: B_hi also meets A_lo
-                    const uint32_t ta1 = tmem_base + bx.a_col1;
+                for (int k = 1; k < 4; ++k) umma_f16_ts(d_tmem, ta0 + 8 * k, bdesc + 2 * k, bx.idesc, 1u);
+                if (bx.a_col1 >= 0) {  // bf16x3: B_hi also meets A_lo
+                  const uint32_t ta1 = tmem_base + bx.a_col1;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) umma_f16_ts(d_tmem, ta1 + 8 * k, bdesc + 2 * k, bx.idesc, 1u);
-                  }
+                  for (int k = 0; k < 4; ++k) umma_f16_ts(d_tmem, ta1 + 8 * k, bdesc + 2 * k, bx.idesc, 1u);
                 }
               }
             }
@@ -532,11 +551,11 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_l0, const __grid_constan
         __syncwarp();
         if (++buf == NACC) { buf = 0; aph ^= 1; }
       }
-      if (elect_one()) umma_commit<1>(a_empty);
+      if (elect_one()) umma_commit<1>(a_empty);  // (arrives at once if this issuer had no tile in the unit)
       __syncwarp();
     }
 #ifdef RCB_DEBUG
-    if (p.prof && lane == 0) {
+    if (p.prof && lane == 0 && me == 0) {
       p.prof[blockIdx.x * 16 + 3] = clock64() - clk0;
       p.prof[blockIdx.x * 16 + 4] = w0;
       p.prof[blockIdx.x * 16 + 5] = w1;
@@ -620,6 +639,7 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_l0, const __grid_constan
         PH_MARK(1);
         release_acc();
         PH_MARK(2);
+        if (RCB_SKIP(p, 128)) continue;  // debug: no epilogue work at all (pure producer + MMA pipeline)
         // scaled first: level 1 is the mean of the STORED level-0 values, bit for bit
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
@@ -933,6 +953,7 @@ int launch_build_tc_packed(const void* ws, size_t ws_bytes, void* const* pyr, co
   p.b_img = b_img;
   p.acc_col0 = (wl.a_words + 127) / 128 * 128;  // A occupies the first a_words TMEM columns
   p.nacc = (512 - p.acc_col0) / BN < MAX_ACC ? (512 - p.acc_col0) / BN : MAX_ACC;
+  p.nacc -= p.nacc % NUM_ISSUERS;  // every issuer keeps to its own accumulators (and sees all of their phases)
 #ifdef RCB_DEBUG
   p.prof = debug_env_ptr("RCB_TC_PROF_PTR");  // device buffer of 16 x 148 uint64 supplied by tools/time_build.py
   p.debug_skip = debug_env_int("RCB_TC_DEBUG_SKIP", 0);
