@@ -15,7 +15,7 @@
 //     RCB_BUILD_BF16X3   bf16 hi/lo, hi*hi + hi*lo + lo*hi, three full-rate passes, error ~5e-6 of max-abs; no range
 //                        restriction (fp16 overflows beyond 65504).
 //     RCB_BUILD_BF16     hi parts only (fast mode, ~2.6e-3).
-//   main kernel   persistent, warp-specialised, 320 threads per CTA, one CTA per SM:
+//   main kernel   persistent, warp-specialised, 352 threads per CTA, one CTA per SM:
 //     warp 0      producer: B tiles (an 8 x 16 PATCH of target pixels x 128 bytes of K = a 16 KB box) stream through an
 //                 mbarrier ring, one box per stage.  The pack kernel writes the target operand as ready-made TILE
 //                 IMAGES -- per (batch, patch) the boxes of the tile's MMA schedule back to back, rows already in the
@@ -23,9 +23,11 @@
 //                 linear cp.async.bulk of 16 contiguous KB.  (Round 1 fetched each box as a 4-D tensor-map box of 128
 //                 rows x 128 B: the TMA unit then spends ~3.3 cycles per row, 1024 rows per tile, and the B stream
 //                 alone took 290 us of the kernel, profiles/r2b_build_anatomy_band_split.txt.)
-//     warp 1      MMA issuer: M = 128 queries x N = 128 targets per instruction, the A operand (queries) lives in
-//                 TENSOR MEMORY for a whole unit (TS form), B through SWIZZLE_128B K-major smem descriptors, fp32
-//                 accumulators in TMEM (double buffered).  The per-tile MMA schedule is a small table (Params::box).
+//     warps 1,10  MMA issuers, alternate tiles: M = 128 queries x N = 128 targets per instruction, the A operand
+//                 (queries) lives in TENSOR MEMORY for a whole unit (TS form), B through SWIZZLE_128B K-major smem
+//                 descriptors, fp32 accumulators in TMEM (two, one per issuer).  The per-tile MMA schedule is a small
+//                 table (Params::box).  Two issuers because the issuing side, not the tensor pipe, paced the MMAs
+//                 (see the comment at the issuer loop).
 //     warps 2-9   epilogue, two warps per TMEM lane quarter (32 queries), split by patch BAND (4 of the 8 patch rows =
 //                 one row of four 4x4 pyramid tiles = 256 contiguous bytes per query): a warp tcgen05.ld's its band
 //                 (lane = query, 64 columns), scales by 1/sqrt(C), stages it as two SWIZZLE_128B boxes
