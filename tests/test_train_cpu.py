@@ -68,3 +68,20 @@ def test_train_step_single_process_equals_reference_loop_body():
         assert torch.allclose(a, b, atol=1e-7)
     assert step.steps_done == 3 and step.allreduce_launches == 0 and set(metrics) == {"epe", "1px", "3px", "5px"}
     step.close()
+
+
+def test_bench_arms_describe_the_same_workload():
+    """`bench.py --impl ours` and `--impl reference` must print the same `config` dict (the driver compares them)."""
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("rcb_bench", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    for name, cfg in bench.CONFIGS.items():
+        a = bench.config_dict(name, cfg, "all-pairs")
+        b = bench.config_dict(name, cfg, "all-pairs")
+        assert a == b and a["workload"].startswith(name) and a["pairs_per_gpu"] == cfg[0]
+    build, lookup, flops = bench.algorithmic_bytes(8, 256, 55, 128, 4, 4)
+    assert build == 2205941760 and lookup == 163553280 and abs(flops - 2.0 * 8 * 7040 * 7040 * 256) < 1  # SURVEY 8(d)
+    assert bench.cpu_sample_pairs(8, 55, 128) == 8 and bench.cpu_sample_pairs(4, 136, 240) == 1
