@@ -889,7 +889,7 @@ def main():
     cfg = CONFIGS[args.config]
     if args.train:
         from raft_optical_flow_b200 import train_bench
-        return train_bench.run(args, cfg, ROOT)
+        return train_bench.run(args, cfg, ROOT, sampler_cls=ClockSampler)
     if args.impl == "reference":
         return run_reference(args, cfg)
     return run_ours(args, cfg)

@@ -35,7 +35,7 @@ def load_reference_raft(root):
     return raft_mod
 
 
-def run(args, cfg, root):
+def run(args, cfg, root, sampler_cls=None):
     import torch
     import torch.distributed as dist
 
@@ -106,7 +106,11 @@ def run(args, cfg, root):
     step_seq = train.TrainStep(model, num_steps=100000, iters=iters, overlap=False)
     per_seq, _ = timed(step_seq, max(3, nsteps // 4))
     step = train.TrainStep(model, num_steps=100000, iters=iters, overlap=True)
+    sampler = sampler_cls(local) if (sampler_cls and rank == 0) else None
+    if sampler:  # clocks / power cap state of the timed region of `value` (the sampler needs ~0.5 s to start: the
+        sampler.start()  # two warm-up steps inside timed() cover it)
     per, total = timed(step, nsteps)
+    clocks = sampler.stop() if sampler else None
     per_e2e, total_e2e = timed(step, nsteps, e2e=True)
     nb = len(step.reducer.buckets) if step.reducer else 0
     launches = step.allreduce_launches
@@ -138,6 +142,7 @@ def run(args, cfg, root):
             # build (pack + main) + iters x (lookup + upsample) forward; iters x (lookup backward + 2 upsample backward)
             # + (L - 1) pool-backward + 4 packs + 2 GEMMs backward
             "gpu_launches": nsteps * (2 + 2 * iters + 3 * iters + (L - 1) + 6),
+            "clocks": clocks,
             "roofline": None,
         }
         print(json.dumps(line))
