@@ -13,14 +13,14 @@
 // version of this kernel was bound by exactly those: ncu L1 data pipe 72 % busy, DRAM 43 %; this one runs at
 // ~80 % of the measured copy bandwidth for the bytes it really moves).  Four tensor maps per level (the nx x ny
 // combinations) live in a host-side plan that is encoded once per pyramid, not per call.
-//   CTA   = 32 consecutive queries of ONE level, 128 threads, a warp owns 8 queries end to end: lane 4i issues
-//           the box of query i on the warp's own mbarrier, the warp waits, then does the math; eight CTAs per SM
-//           keep ~100 KB of gathers in flight.
-//   math  = the 4 lanes of a query split the (2r+1) y offsets; a lane reads its 3-4 window rows as whole tile
+//   CTA   = 32 consecutive queries of ONE level, 2 lanes per query (64 threads), a warp owns 16 queries end to
+//           end: the first lane of a query issues its box on the warp's own mbarrier, the warp waits, then does
+//           the math; eight CTAs per SM keep ~100 KB of gathers in flight.
+//   math  = the lanes of a query split the (2r+1) y offsets; a lane reads its 5-6 window rows as whole tile
 //           rows (LDS.128), aligns them to the window's 4-byte phase with two select stages, applies the separable
 //           bilinear weights horizontally, then vertically against the previous row (all (2r+1)^2 samples of a
 //           level share one fractional offset because the window offsets are integers).
-//   store = one instruction writes 4 channels x 8 consecutive queries (full 32-byte sectors).
+//   store = one instruction writes 2 channels x 16 consecutive queries (64-byte runs).
 // Padding INSIDE edge tiles (rows >= H_l, columns >= W_l of the last tile row/column) is unspecified in the
 // layout, so those taps are masked here; everything outside the tile grid is zero-filled by the TMA unit.
 #include <cstdlib>
@@ -41,29 +41,39 @@ namespace rcb {
 // then it uses a single pixel row of it.  The TMA box is therefore always 3 tile rows (12 tiles, 768-byte slots instead
 // of 1024) and that one pixel row -- 16 bytes per tile -- is fetched with cp.async into 64 bytes per query.  The
 // smaller slots let 8 CTAs share an SM instead of 6 (36 -> 33 us at cfg2) and the window touches fewer sectors.
-template <int R>
-__global__ void __launch_bounds__(TmaCfg<R>::THREADS, 8)
-lookup_tma_kernel(const __grid_constant__ LookupMaps maps, PyramidDev pyr, const float* __restrict__ coords,
-                  float* __restrict__ out, int Q, int L, int dbg) {
+// Lanes per query of the fp32 lookup kernel (they split the (2r+1) window rows).  2 instead of 4 halves the per-query
+// prologue (coordinates, window phase, TMA issue) every lane executes: ~35 % fewer instructions per launch.  In a short
+// loop the kernel is DRAM-bound either way (33.2 us at cfg2); under sustained load the board runs at its power cap and
+// the leaner kernel leaves the SM clock higher: whole step 1914 -> 1866 us on the same GPU.
+#ifndef RCB_LOOKUP_LPQ
+#define RCB_LOOKUP_LPQ 2
+#endif
+constexpr int kLookupLPQ = RCB_LOOKUP_LPQ;
+static_assert(kLookupLPQ == 2 || kLookupLPQ == 4, "lanes per query");
+
+template <int R, int LPQ>
+__global__ void __launch_bounds__(TmaCfg<R>::QT * LPQ, 8)
+lookup_tma_kernel(const __grid_constant__ LookupMaps maps, const __grid_constant__ PyramidDev pyr,
+                  const float* __restrict__ coords, float* __restrict__ out, int Q, int L, int dbg) {
   using Cfg = TmaCfg<R>;
   constexpr int RD = Cfg::RD, ROWS = Cfg::ROWS, NMIN = Cfg::NMIN, NMAX = Cfg::NMAX;
-  constexpr int NBMAX = Cfg::NBMAX, QT = Cfg::QT;
+  constexpr int QT = Cfg::QT, THREADS = QT * LPQ;
+  constexpr int NBMAX = (RD + LPQ - 1) / LPQ;    // output rows per lane
   constexpr bool XROW = R == 4;
   constexpr int NYBOX = XROW ? NMAX - 1 : NMAX;  // tile rows a box can have
   constexpr int SLOT16 = XROW ? (NMAX * NYBOX * 64 + 127) / 128 * 8 : Cfg::SLOT16;
   __shared__ __align__(128) float4 slots[QT * SLOT16];
   __shared__ __align__(16) float4 xrow[XROW ? QT * 4 : 1];  // [query][tile]: pixel row 0 of the 4th tile row
-  __shared__ __align__(8) unsigned long long bars[Cfg::THREADS / 32];
+  __shared__ __align__(8) unsigned long long bars[THREADS / 32];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int l = blockIdx.y;
   const int b = blockIdx.z;
-  const int ql = tid >> 2, sub = tid & 3;
+  const int ql = tid / LPQ, sub = tid % LPQ;
   const int q = blockIdx.x * QT + ql;
   const bool q_ok = q < Q;
-  // (selects instead of pyr.H[l]: a dynamically indexed by-value parameter array is copied to local memory)
-  const int Hl = l == 0 ? pyr.H[0] : l == 1 ? pyr.H[1] : l == 2 ? pyr.H[2] : pyr.H[3];
-  const int Wl = l == 0 ? pyr.W[0] : l == 1 ? pyr.W[1] : l == 2 ? pyr.W[2] : pyr.W[3];
+  // (pyr is a __grid_constant__ parameter: indexing it by the level is an indexed constant-bank load, not a local copy)
+  const int Hl = pyr.H[l], Wl = pyr.W[l];
   float cx = -1.0e6f, cy = -1.0e6f;
   if (q_ok) {
     cx = __ldg(coords + (long long)(b * 2 + 0) * Q + q);
@@ -79,7 +89,7 @@ lookup_tma_kernel(const __grid_constant__ LookupMaps maps, PyramidDev pyr, const
   pdl_launch_dependents();
   const uint32_t bar = smem_u32(&bars[warp]);
   if (lane == 0) {
-    mbar_init(bar, 8);
+    mbar_init(bar, 32 / LPQ);
     fence_barrier_init();
   }
   __syncwarp();
@@ -93,23 +103,30 @@ lookup_tma_kernel(const __grid_constant__ LookupMaps maps, PyramidDev pyr, const
     }
   }
   if (XROW) {
-    if (q_ok && ny > NYBOX && sub < nx) {  // lane `sub` fetches the row piece of tile `sub`
-      const float* pl = static_cast<const float*>(l == 0 ? pyr.ptr[0] : l == 1 ? pyr.ptr[1] : l == 2 ? pyr.ptr[2] : pyr.ptr[3]);
-      const int txs = l == 0 ? pyr.tiles_x[0] : l == 1 ? pyr.tiles_x[1] : l == 2 ? pyr.tiles_x[2] : pyr.tiles_x[3];
-      const long long ps = l == 0 ? pyr.plane_stride[0] : l == 1 ? pyr.plane_stride[1] : l == 2 ? pyr.plane_stride[2]
-                                                                                              : pyr.plane_stride[3];
-      const int ty = (lc.ys >> 2) + NYBOX, tx = (lc.xs >> 2) + sub;
-      const bool in = ty >= 0 && ty * 4 < Hl && tx >= 0 && tx < txs;  // tiles outside the grid read as zeros
-      const float* src = pl + ((long long)b * Q + q) * ps + (in ? ((long long)(ty * txs + tx) << 4) : 0);
-      cp_async16_zfill(smem_u32(xrow + ql * 4 + sub), src, in ? 16 : 0);
+    if (q_ok && ny > NYBOX && sub < nx) {  // the lanes of the query fetch the row pieces of its nx tiles
+      const float* pl = static_cast<const float*>(pyr.ptr[l]);
+      const int txs = pyr.tiles_x[l];
+      const long long ps = pyr.plane_stride[l];
+      const int ty = (lc.ys >> 2) + NYBOX;
+      const float* plane = pl + ((long long)b * Q + q) * ps;
+#pragma unroll
+      for (int t = sub; t < NMAX; t += LPQ) {
+        if (t < nx) {
+          const int tx = (lc.xs >> 2) + t;
+          const bool in = ty >= 0 && ty * 4 < Hl && tx >= 0 && tx < txs;  // tiles outside the grid read as zeros
+          cp_async16_zfill(smem_u32(xrow + ql * 4 + t), plane + (in ? ((long long)(ty * txs + tx) << 4) : 0), in ? 16 : 0);
+        }
+      }
     }
     cp_async_commit();
   }
   if (!q_ok) return;
   const float fx = lc.fx, fy = lc.fy, gx = 1.0f - lc.fx, gy = 1.0f - lc.fy;
-  const int b0 = (RD * sub) >> 2, nb = ((RD * (sub + 1)) >> 2) - b0;  // output rows [b0, b0 + nb), nb <= NBMAX
+  const int b0 = (RD * sub) / LPQ, nb = (RD * (sub + 1)) / LPQ - b0;  // output rows [b0, b0 + nb), nb <= NBMAX
   float* o = out + (((long long)b * L + l) * RD * RD + b0) * Q + q;   // channel = a * RD + b
-  const long long sa = (long long)RD * Q;
+  int offa[RD];  // channel offset of x offset a (one level's window of one pair is < 2^31 elements, see plan_init)
+#pragma unroll
+  for (int a = 0; a < RD; ++a) offa[a] = a * RD * Q;
   const float4* slot = slots + ql * SLOT16;
   const bool ragged_w = (Wl & 3) != 0;
   mbar_wait(bar, 0);
@@ -153,7 +170,7 @@ lookup_tma_kernel(const __grid_constant__ LookupMaps maps, PyramidDev pyr, const
     if (jj > 0) {
       if (jj == 1) pdl_wait();  // nothing is written before the preceding kernel of the stream has completed
 #pragma unroll
-      for (int a = 0; a < RD; ++a) o[a * sa] = gy * hp[a] + fy * h[a];
+      for (int a = 0; a < RD; ++a) o[offa[a]] = gy * hp[a] + fy * h[a];
       o += Q;
     }
 #pragma unroll
@@ -288,6 +305,8 @@ static int plan_init(LookupPlan* plan, const void* const* pyr, const rcb_pyramid
   const int rows = 2 * radius + 2;
   const int nminx = f16 ? (rows + 7) >> 3 : (rows + 3) >> 2, nminy = (rows + 3) >> 2;
   const long long planes = (long long)B * H * W;
+  // the kernels index the window channels of one pair and level with 32-bit offsets
+  if ((long long)H * W * (2 * radius + 1) * (2 * radius + 1) > 0x7fffffffLL) return RCB_ERR_UNSUPPORTED;
   for (int l = 0; l < lay.levels; ++l) {
     for (int sel = 0; sel < 4; ++sel) {
       const int nx = nminx + (sel & 1), ny = nminy + (sel >> 1);
@@ -335,11 +354,12 @@ static int launch_lookup_tma_r(const LookupPlan& plan, const PyramidDev& pd, con
   const int Q = plan.H * plan.W;
   dim3 grid((Q + Cfg::QT - 1) / Cfg::QT, plan.lay.levels, plan.B);
   static const int dbg = debug_env_int("RCB_LOOKUP_DEBUG", 0);  // RCB_DEBUG builds only
-  cudaLaunchConfig_t cfg = pdl_config(grid, Cfg::THREADS, s);
+  cudaLaunchConfig_t cfg = pdl_config(grid, Cfg::QT * kLookupLPQ, s);
   cudaLaunchAttribute attr[1];
   cfg.numAttrs = pdl_attribute(attr);
   cfg.attrs = attr;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, lookup_tma_kernel<R>, plan.maps, pd, coords, out, Q, (int)plan.lay.levels, dbg);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, lookup_tma_kernel<R, kLookupLPQ>, plan.maps, pd, coords, out, Q,
+                                     (int)plan.lay.levels, dbg);
   if (e != cudaSuccess) return (int)e;
   return launch_status();
 }
