@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define RCB_ABI_VERSION 8
+#define RCB_ABI_VERSION 9
 #define RCB_MAX_LEVELS 4 /* core/raft.py:46-53 fixes corr_levels = 4 */
 #define RCB_MAX_RADIUS 4 /* core/raft.py:47,53: radius 3 (small) / 4 (full) */
 
@@ -136,6 +136,11 @@ RCB_API size_t rcb_corr_lookup_plan_bytes(void);
 RCB_API int rcb_corr_lookup_plan_init(void* plan, size_t plan_bytes, const void* const* pyr, int B, int H, int W,
                               int levels, int radius, int pyr_dtype);
 RCB_API int rcb_corr_lookup_planned(const void* plan, const float* coords, float* out, rcb_stream_t stream);
+/* Tuning knob of the fp32 lookup kernel: how many lanes share one query's window.  0 (what plan_init sets) lets the
+ * launch choose -- 2 for grids of several waves (fewest instructions: the kernel is DRAM-bound and the board runs at
+ * its power cap), 4 for grids that do not fill the GPU twice (latency-bound) --; 2 or 4 pins it.  Results are
+ * identical bit for bit. */
+RCB_API int rcb_corr_lookup_plan_set_lanes(void* plan, int lanes_per_query);
 
 /* ---- K4: backward of the all-pairs path ---------------------------------------------------
  * Replaces what autograd records through core/corr.py:25-127 for train.py:212.

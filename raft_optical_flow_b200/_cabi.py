@@ -13,7 +13,7 @@ if os.environ.get("RCB_USE_DEBUG_LIB") == "1":  # timing / profiling hooks (tool
 if os.environ.get("RCB_LIB_VARIANT"):  # A/B builds of build.py --variant (debug-hook builds with compile-time switches)
     LIB_PATH = os.path.join(HERE, f"libraftcorr_b200_{os.environ['RCB_LIB_VARIANT']}.so")
 
-ABI_VERSION = 8
+ABI_VERSION = 9
 MAX_LEVELS = 4
 MAX_RADIUS = 4
 
@@ -54,6 +54,7 @@ SIGNATURES = {
     "rcb_corr_lookup_plan_bytes": (ctypes.c_size_t, []),
     "rcb_corr_lookup_plan_init": (_i, [_vp, ctypes.c_size_t, ctypes.POINTER(_vp), _i, _i, _i, _i, _i, _i]),
     "rcb_corr_lookup_planned": (_i, [_vp, _vp, _vp, _vp]),
+    "rcb_corr_lookup_plan_set_lanes": (_i, [_vp, _i]),
     "rcb_corr_lookup_backward": (_i, [ctypes.POINTER(_vp), _vp, _vp, ctypes.POINTER(_vp), _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "rcb_corr_pool_backward": (_i, [ctypes.POINTER(_vp), _i, _i, _i, _i, _vp]),
     "rcb_corr_contract_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
@@ -122,3 +123,7 @@ class LookupPlan:
         self.nbytes = n
         check(lib().rcb_corr_lookup_plan_init(self.ptr, n, ptrs, B, H, W, levels, radius, dtype),
               "rcb_corr_lookup_plan_init")
+
+    def set_lanes(self, lanes):
+        """Pins the lanes per query of the fp32 lookup kernel (2 or 4; 0 = chosen per launch from the grid size)."""
+        check(lib().rcb_corr_lookup_plan_set_lanes(self.ptr, lanes), "rcb_corr_lookup_plan_set_lanes")

@@ -99,6 +99,8 @@ int rcb_corr_lookup_plan_init(void* plan, size_t plan_bytes, const void* const* 
   return lookup_plan_init(plan, plan_bytes, pyr, lay, B, H, W, radius);
 }
 
+int rcb_corr_lookup_plan_set_lanes(void* plan, int lanes_per_query) { return lookup_plan_set_lanes(plan, lanes_per_query); }
+
 int rcb_corr_lookup_planned(const void* plan, const float* coords, float* out, rcb_stream_t stream) {
   if (!plan || !coords || !out) return RCB_ERR_INVALID_ARGUMENT;
   return launch_lookup_planned(plan, coords, out, reinterpret_cast<cudaStream_t>(stream));

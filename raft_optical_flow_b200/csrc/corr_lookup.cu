@@ -41,15 +41,19 @@ namespace rcb {
 // then it uses a single pixel row of it.  The TMA box is therefore always 3 tile rows (12 tiles, 768-byte slots instead
 // of 1024) and that one pixel row -- 16 bytes per tile -- is fetched with cp.async into 64 bytes per query.  The
 // smaller slots let 8 CTAs share an SM instead of 6 (36 -> 33 us at cfg2) and the window touches fewer sectors.
-// Lanes per query of the fp32 lookup kernel (they split the (2r+1) window rows).  2 instead of 4 halves the per-query
-// prologue (coordinates, window phase, TMA issue) every lane executes: ~35 % fewer instructions per launch.  In a short
-// loop the kernel is DRAM-bound either way (33.2 us at cfg2); under sustained load the board runs at its power cap and
-// the leaner kernel leaves the SM clock higher: whole step 1914 -> 1866 us on the same GPU.
+//
+// Lanes per query of the fp32 lookup kernel (they split the (2r+1) window rows): 2 for grids of several waves, 4 for
+// small ones (rcb_corr_lookup_plan_set_lanes pins it).  Two lanes halve the per-query prologue (coordinates, window phase, TMA issue) every lane executes: 26 %
+// fewer instructions per launch.  In a short loop the kernel is DRAM-bound either way (33.2 us at cfg2); under
+// sustained load the board runs at its power cap and the leaner kernel leaves the SM clock higher: whole step
+// 1914 -> 1866 us on the same GPU.  A grid that does not fill the GPU twice is latency-bound
+// instead (cfg1: one frame pair, 880 CTAs): there four lanes finish a query sooner (6.9 against 8.9 us per launch).
+// RCB_LOOKUP_LPQ = 2 or 4 pins the choice (A/B builds).
 #ifndef RCB_LOOKUP_LPQ
-#define RCB_LOOKUP_LPQ 2
+#define RCB_LOOKUP_LPQ 0
 #endif
 constexpr int kLookupLPQ = RCB_LOOKUP_LPQ;
-static_assert(kLookupLPQ == 2 || kLookupLPQ == 4, "lanes per query");
+static_assert(kLookupLPQ == 0 || kLookupLPQ == 2 || kLookupLPQ == 4, "lanes per query");
 
 template <int R, int LPQ>
 __global__ void __launch_bounds__(TmaCfg<R>::QT * LPQ, 8)
@@ -326,6 +330,7 @@ static int plan_init(LookupPlan* plan, const void* const* pyr, const rcb_pyramid
   }
   plan->lay = lay;
   plan->B = B; plan->H = H; plan->W = W; plan->radius = radius;
+  plan->lanes = 0;
   plan->magic = kPlanMagic;
   return RCB_OK;
 }
@@ -354,12 +359,17 @@ static int launch_lookup_tma_r(const LookupPlan& plan, const PyramidDev& pd, con
   const int Q = plan.H * plan.W;
   dim3 grid((Q + Cfg::QT - 1) / Cfg::QT, plan.lay.levels, plan.B);
   static const int dbg = debug_env_int("RCB_LOOKUP_DEBUG", 0);  // RCB_DEBUG builds only
-  cudaLaunchConfig_t cfg = pdl_config(grid, Cfg::QT * kLookupLPQ, s);
+  // two waves of 8 CTAs per SM on 148 SMs
+  const bool small = (long long)grid.x * grid.y * grid.z <= 2LL * 148 * 8;
+  const int lpq = kLookupLPQ ? kLookupLPQ : plan.lanes ? plan.lanes : (small ? 4 : 2);
+  cudaLaunchConfig_t cfg = pdl_config(grid, Cfg::QT * lpq, s);
   cudaLaunchAttribute attr[1];
   cfg.numAttrs = pdl_attribute(attr);
   cfg.attrs = attr;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, lookup_tma_kernel<R, kLookupLPQ>, plan.maps, pd, coords, out, Q,
-                                     (int)plan.lay.levels, dbg);
+  cudaError_t e = lpq == 4 ? cudaLaunchKernelEx(&cfg, lookup_tma_kernel<R, 4>, plan.maps, pd, coords, out, Q,
+                                                (int)plan.lay.levels, dbg)
+                           : cudaLaunchKernelEx(&cfg, lookup_tma_kernel<R, 2>, plan.maps, pd, coords, out, Q,
+                                                (int)plan.lay.levels, dbg);
   if (e != cudaSuccess) return (int)e;
   return launch_status();
 }
@@ -386,6 +396,14 @@ int lookup_plan_init(void* plan, size_t plan_bytes, const void* const* pyr, cons
   if (!plan || plan_bytes < sizeof(LookupPlan) || (reinterpret_cast<uintptr_t>(plan) & 63))
     return RCB_ERR_INVALID_ARGUMENT;
   return plan_init(static_cast<LookupPlan*>(plan), pyr, lay, B, H, W, radius);
+}
+
+int lookup_plan_set_lanes(void* plan_, int lanes) {
+  LookupPlan* plan = static_cast<LookupPlan*>(plan_);
+  if (!plan || (reinterpret_cast<uintptr_t>(plan_) & 63) || plan->magic != kPlanMagic) return RCB_ERR_INVALID_ARGUMENT;
+  if (lanes != 0 && lanes != 2 && lanes != 4) return RCB_ERR_INVALID_ARGUMENT;
+  plan->lanes = lanes;
+  return RCB_OK;
 }
 
 int launch_lookup_planned(const void* plan_, const float* coords, float* out, cudaStream_t s) {

@@ -37,6 +37,7 @@ struct LookupPlan {  // host-side blob behind rcb_corr_lookup_plan_*
   rcb_pyramid_layout lay;
   const void* ptr[RCB_MAX_LEVELS];
   int B, H, W, radius;
+  int lanes;  // lanes per query of the fp32 kernel: 0 = chosen per launch from the grid size, 2 or 4 = pinned
   uint32_t magic;
 };
 constexpr uint32_t kPlanMagic = 0x52434250u;  // "RCBP"

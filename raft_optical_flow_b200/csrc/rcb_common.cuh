@@ -140,6 +140,7 @@ size_t lookup_plan_bytes();
 int lookup_plan_init(void* plan, size_t plan_bytes, const void* const* pyr, const rcb_pyramid_layout& lay, int B,
                      int H, int W, int radius);
 int launch_lookup_planned(const void* plan, const float* coords, float* out, cudaStream_t s);
+int lookup_plan_set_lanes(void* plan, int lanes);
 int launch_lookup_backward(const void* const* pyr, const rcb_pyramid_layout& lay, const float* coords,
                            const float* grad_out, float* const* dpyr, float* dcoords, int B, int H, int W,
                            int radius, cudaStream_t s);

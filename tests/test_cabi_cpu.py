@@ -27,14 +27,14 @@ def header_symbols():
 
 def test_library_exports_every_declared_symbol(lib):
     syms = header_symbols()
-    assert len(syms) == 26
+    assert len(syms) == 27
     for s in syms:
         assert hasattr(lib, s), s
     assert sorted(_cabi.SIGNATURES) == syms  # the ctypes table binds exactly the header
 
 
 def test_status_strings(lib):
-    assert lib.rcb_abi_version() == 8
+    assert lib.rcb_abi_version() == 9
     assert lib.rcb_status_string(0) == b"ok"
     assert b"invalid" in lib.rcb_status_string(-1)
     assert b"unsupported" in lib.rcb_status_string(-2)

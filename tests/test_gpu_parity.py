@@ -703,6 +703,35 @@ def test_lookup_sweep_of_small_geometries_vs_oracle(rcb, dev, orc, seed):
         got = blk(t(coords, dev)).cpu().numpy()
         assert np.isfinite(got).all()
         assert rel_err(got, want) < tol, (seed, pdt, B, C, H, W, r, L)
+        if pdt == "f32":  # both lane mappings of the fp32 kernel (grids this small run 4 lanes per query by default)
+            for lanes in (2, 4):
+                blk._state.plan.set_lanes(lanes)
+                assert np.array_equal(blk(t(coords, dev)).cpu().numpy(), got), (seed, lanes)
+
+
+@pytest.mark.parametrize("r,L", [(1, 2), (2, 3), (3, 4), (4, 4)])
+def test_lookup_lanes_per_query_are_bit_identical(rcb, dev, orc, r, L):
+    """rcb_corr_lookup_plan_set_lanes: the two lane mappings of the lookup kernel (2 lanes per query for grids of
+    several waves, 4 for small ones) are the same arithmetic in the same order; ragged width, windows beyond every
+    border, every radius; and the set_lanes argument is validated."""
+    rs = np.random.RandomState(77 + r)
+    B, C, H, W = 2, 16, 27, 37
+    f1 = rs.standard_normal((B, C, H, W)).astype(np.float32)
+    f2 = rs.standard_normal((B, C, H, W)).astype(np.float32)
+    ys, xs = np.meshgrid(np.arange(H), np.arange(W), indexing="ij")
+    coords = (np.stack([xs, ys])[None] + 6.0 * rs.standard_normal((B, 2, H, W))).astype(np.float32)
+    coords[:, 0, 0, :] = np.linspace(-15.0, W + 14.0, W, dtype=np.float32)
+    coords[:, 1, :, 0] = np.linspace(-15.0, H + 14.0, H, dtype=np.float32)
+    blk = rcb.CorrBlock(t(f1, dev), t(f2, dev), num_levels=L, radius=r)
+    want = orc.OracleCorrBlock(f1, f2, num_levels=L, radius=r)(coords, roundtrip=False)
+    outs = {}
+    for lanes in (0, 2, 4):
+        blk._state.plan.set_lanes(lanes)
+        outs[lanes] = blk(t(coords, dev)).cpu().numpy()
+        assert rel_err(outs[lanes], want) < TOL, (lanes, r, L)
+    assert np.array_equal(outs[2], outs[4]) and np.array_equal(outs[0], outs[4])
+    with pytest.raises(RuntimeError):
+        blk._state.plan.set_lanes(3)
 
 
 # ---------------------------------------------------------------------------------------------
