@@ -1,5 +1,5 @@
 """On-GPU cross-check of the tcgen05 build modes against the fp32 SIMT build (level by level).
-    python tools/check_tc.py            # several shapes; RCB_TC_NCTA=2 selects the cta_group::2 pair kernel"""
+    python tools/check_tc.py            # several shapes"""
 import os
 import sys
 
@@ -23,7 +23,7 @@ for direct in ("0",):
                 got = CorrBlock(f1, f2, num_levels=L, radius=4, mode=mode).corr_pyramid
                 torch.cuda.synchronize()
             except Exception as e:  # noqa: BLE001
-                print(f"ncta={os.environ.get("RCB_TC_NCTA", "1")} {mode} {(B, C, H, W, L)}: EXCEPTION {e}")
+                print(f"{mode} {(B, C, H, W, L)}: EXCEPTION {e}")
                 ok = False
                 raise SystemExit(1)
             errs = []
@@ -36,7 +36,7 @@ for direct in ("0",):
                     bad = ((r - t).abs() > tol * r.abs().max()).nonzero()
                     print(f"   level {l}: {bad.shape[0]} bad of {r.numel()}, first {bad[:6].tolist()}, "
                           f"nan={torch.isnan(t).sum().item()}")
-            print(f"ncta={os.environ.get("RCB_TC_NCTA", "1")} {mode:7s} {str((B, C, H, W, L)):24s} rel err per level:",
+            print(f"{mode:7s} {str((B, C, H, W, L)):24s} rel err per level:",
                   " ".join(f"{e:.2e}" for e in errs), "OK" if all(e < tol for e in errs) else "FAIL")
 print("ALL OK" if ok else "SOME FAILED")
 sys.exit(0 if ok else 1)
