@@ -691,18 +691,24 @@ def graph_step_timing(torch, CorrBlock, dev, f, dev_c, L, r, iters, args, mx, wo
         for _ in range(3):
             g.replay()
         torch.cuda.synchronize(dev)
-        n = max(5, min(200, int(0.25 / 2e-3)))
-        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a0.record()
-        for _ in range(n):
-            g.replay()
-        a1.record()
-        torch.cuda.synchronize(dev)
-        ms = mx([a0.elapsed_time(a1) / n])[0]
+        # timed like `value`: blocks of replays until >= MIN_TIMED_S, median block -- a quarter of a second would end
+        # before the power cap has pulled the clock down and flatter the graph by 3-4 %
+        n, blocks, total = 20, [], 0.0
+        while total < MIN_TIMED_S * 1e3 and len(blocks) < 200:
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            for _ in range(n):
+                g.replay()
+            a1.record()
+            torch.cuda.synchronize(dev)
+            blocks.append(a0.elapsed_time(a1) / n)
+            total = mx([total + a0.elapsed_time(a1)])[0]
+        ms = mx([statistics.median(blocks)])[0]
         del g, outs, blk, out
         torch.cuda.empty_cache()
-        return {"ms_per_step": ms, "value": world * B / (ms * 1e-3), "unit": "pairs/s", "replays": n,
-                "note": "one graph = pack + build + all lookups of a step (every lookup keeps its own output tensor)"}
+        return {"ms_per_step": ms, "value": world * B / (ms * 1e-3), "unit": "pairs/s", "replays": n * len(blocks),
+                "note": "one graph = pack + build + all lookups of a step (every lookup keeps its own output tensor); "
+                        "median of blocks of 20 replays over >= 1 s, as for `value`"}
     except Exception as e:  # noqa: BLE001 -- an optional figure must not take the headline down
         return {"error": f"{type(e).__name__}: {e}"[:200]}
 
