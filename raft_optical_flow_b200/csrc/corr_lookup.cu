@@ -197,24 +197,24 @@ struct TmaCfgH {
   static constexpr int QT = 32, THREADS = 128;
 };
 
-template <int R>
-__global__ void __launch_bounds__(TmaCfgH<R>::THREADS, 8)
-lookup_tma_f16_kernel(const __grid_constant__ LookupMaps maps, PyramidDev pyr, const float* __restrict__ coords,
-                      float* __restrict__ out, int Q, int L) {
+template <int R, int LPQ>
+__global__ void __launch_bounds__(TmaCfgH<R>::QT * LPQ, 8)
+lookup_tma_f16_kernel(const __grid_constant__ LookupMaps maps, const __grid_constant__ PyramidDev pyr,
+                      const float* __restrict__ coords, float* __restrict__ out, int Q, int L) {
   using Cfg = TmaCfgH<R>;
   constexpr int RD = Cfg::RD, ROWS = Cfg::ROWS, NMINX = Cfg::NMINX, NMAXX = Cfg::NMAXX, NMINY = Cfg::NMINY;
-  constexpr int SLOT16 = Cfg::SLOT16, NBMAX = Cfg::NBMAX, QT = Cfg::QT;
+  constexpr int SLOT16 = Cfg::SLOT16, QT = Cfg::QT, THREADS = QT * LPQ;
+  constexpr int NBMAX = (RD + LPQ - 1) / LPQ;  // output rows per lane
   __shared__ __align__(128) uint4 slots[QT * SLOT16];
-  __shared__ __align__(8) unsigned long long bars[Cfg::THREADS / 32];
+  __shared__ __align__(8) unsigned long long bars[THREADS / 32];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int l = blockIdx.y;
   const int b = blockIdx.z;
-  const int ql = tid >> 2, sub = tid & 3;
+  const int ql = tid / LPQ, sub = tid % LPQ;
   const int q = blockIdx.x * QT + ql;
   const bool q_ok = q < Q;
-  const int Hl = l == 0 ? pyr.H[0] : l == 1 ? pyr.H[1] : l == 2 ? pyr.H[2] : pyr.H[3];
-  const int Wl = l == 0 ? pyr.W[0] : l == 1 ? pyr.W[1] : l == 2 ? pyr.W[2] : pyr.W[3];
+  const int Hl = pyr.H[l], Wl = pyr.W[l];
   float cx = -1.0e6f, cy = -1.0e6f;
   if (q_ok) {
     cx = __ldg(coords + (long long)(b * 2 + 0) * Q + q);
@@ -227,7 +227,7 @@ lookup_tma_f16_kernel(const __grid_constant__ LookupMaps maps, PyramidDev pyr, c
   pdl_launch_dependents();
   const uint32_t bar = smem_u32(&bars[warp]);
   if (lane == 0) {
-    mbar_init(bar, 8);
+    mbar_init(bar, 32 / LPQ);
     fence_barrier_init();
   }
   __syncwarp();
@@ -242,9 +242,11 @@ lookup_tma_f16_kernel(const __grid_constant__ LookupMaps maps, PyramidDev pyr, c
   }
   if (!q_ok) return;
   const float fx = lc.fx, fy = lc.fy, gx = 1.0f - lc.fx, gy = 1.0f - lc.fy;
-  const int b0 = (RD * sub) >> 2, nb = ((RD * (sub + 1)) >> 2) - b0;  // output rows [b0, b0 + nb), nb <= NBMAX
+  const int b0 = (RD * sub) / LPQ, nb = (RD * (sub + 1)) / LPQ - b0;  // output rows [b0, b0 + nb), nb <= NBMAX
   float* o = out + (((long long)b * L + l) * RD * RD + b0) * Q + q;   // channel = a * RD + b
-  const long long sa = (long long)RD * Q;
+  int offa[RD];  // channel offset of x offset a (< 2^31 elements, see plan_init)
+#pragma unroll
+  for (int a = 0; a < RD; ++a) offa[a] = a * RD * Q;
   const uint4* slot = slots + ql * SLOT16;
   const bool ragged_w = (Wl & 7) != 0;
   constexpr int NP = (ROWS / 2 + 3) / 2;                 // 8-byte pairs that cover ROWS / 2 + 2 words
@@ -293,7 +295,7 @@ lookup_tma_f16_kernel(const __grid_constant__ LookupMaps maps, PyramidDev pyr, c
     if (jj > 0) {
       if (jj == 1) pdl_wait();  // nothing is written before the preceding kernel of the stream has completed
 #pragma unroll
-      for (int a = 0; a < RD; ++a) o[a * sa] = gy * hp[a] + fy * h[a];
+      for (int a = 0; a < RD; ++a) o[offa[a]] = gy * hp[a] + fy * h[a];
       o += Q;
     }
 #pragma unroll
@@ -380,11 +382,16 @@ static int launch_lookup_tma_f16_r(const LookupPlan& plan, const PyramidDev& pd,
   using Cfg = TmaCfgH<R>;
   const int Q = plan.H * plan.W;
   dim3 grid((Q + Cfg::QT - 1) / Cfg::QT, plan.lay.levels, plan.B);
-  cudaLaunchConfig_t cfg = pdl_config(grid, Cfg::THREADS, s);
+  const bool small = (long long)grid.x * grid.y * grid.z <= 2LL * 148 * 8;
+  const int lpq = kLookupLPQ ? kLookupLPQ : plan.lanes ? plan.lanes : (small ? 4 : 2);
+  cudaLaunchConfig_t cfg = pdl_config(grid, Cfg::QT * lpq, s);
   cudaLaunchAttribute attr[1];
   cfg.numAttrs = pdl_attribute(attr);
   cfg.attrs = attr;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, lookup_tma_f16_kernel<R>, plan.maps, pd, coords, out, Q, (int)plan.lay.levels);
+  cudaError_t e = lpq == 4 ? cudaLaunchKernelEx(&cfg, lookup_tma_f16_kernel<R, 4>, plan.maps, pd, coords, out, Q,
+                                                (int)plan.lay.levels)
+                           : cudaLaunchKernelEx(&cfg, lookup_tma_f16_kernel<R, 2>, plan.maps, pd, coords, out, Q,
+                                                (int)plan.lay.levels);
   if (e != cudaSuccess) return (int)e;
   return launch_status();
 }

@@ -711,16 +711,17 @@ def test_lookup_lanes_per_query_are_bit_identical(rcb, dev, orc, r, L):
     coords = (np.stack([xs, ys])[None] + 6.0 * rs.standard_normal((B, 2, H, W))).astype(np.float32)
     coords[:, 0, 0, :] = np.linspace(-15.0, W + 14.0, W, dtype=np.float32)
     coords[:, 1, :, 0] = np.linspace(-15.0, H + 14.0, H, dtype=np.float32)
-    blk = rcb.CorrBlock(t(f1, dev), t(f2, dev), num_levels=L, radius=r)
     want = orc.OracleCorrBlock(f1, f2, num_levels=L, radius=r)(coords, roundtrip=False)
-    outs = {}
-    for lanes in (0, 2, 4):
-        blk._state.plan.set_lanes(lanes)
-        outs[lanes] = blk(t(coords, dev)).cpu().numpy()
-        assert rel_err(outs[lanes], want) < TOL, (lanes, r, L)
-    assert np.array_equal(outs[2], outs[4]) and np.array_equal(outs[0], outs[4])
-    with pytest.raises(RuntimeError):
-        blk._state.plan.set_lanes(3)
+    for pdt, tol in (("f32", TOL), ("f16", 2e-3)):  # the fp32 kernel and the fp16-pyramid kernel of the fast mode
+        blk = rcb.CorrBlock(t(f1, dev), t(f2, dev), num_levels=L, radius=r, pyramid_dtype=pdt)
+        outs = {}
+        for lanes in (0, 2, 4):
+            blk._state.plan.set_lanes(lanes)
+            outs[lanes] = blk(t(coords, dev)).cpu().numpy()
+            assert rel_err(outs[lanes], want) < tol, (pdt, lanes, r, L)
+        assert np.array_equal(outs[2], outs[4]) and np.array_equal(outs[0], outs[4])
+        with pytest.raises(RuntimeError):
+            blk._state.plan.set_lanes(3)
 
 
 # ---------------------------------------------------------------------------------------------
