@@ -1,5 +1,7 @@
 #!/bin/bash
 # A/B of lookup kernel variants (lanes per query, FFMA2): parity, burst and sustained timing.
+# The variant libraries are built first, here: python -m raft_optical_flow_b200.build --variant lpq2b -DRCB_LOOKUP_LPQ=2
+# (lpq2c: + -DRCB_LOOKUP_FFMA2=1, since removed from the source; lpq4c: -DRCB_LOOKUP_LPQ=4).
 out=gpurun_out/lpq_ab2.txt
 : > $out
 echo "### parity (lpq2c library)" >> $out
