@@ -1,11 +1,17 @@
 #!/bin/bash
-# Sustained (power-capped) anatomy of the build: which part draws the power?  RCB_DEBUG library, skip bits of
-# corr_build_tc.cu: 16 no B loads, 32 no MMAs, 64 no tmem_ld, 8 no level-0 stores, 128 no epilogue at all.
-out=gpurun_out/power_build_anatomy.txt
+# Round 1's kernel (libraftcorr_b200_r1.so built from commit ed8c101), single-CTA MMAs against cta_group::2 pairs,
+# in a burst and under sustained load: is halving the B bytes delivered per SM worth the pair's barrier traffic?
+out=gpurun_out/r1_ncta_ab.txt
 : > $out
-export RCB_USE_DEBUG_LIB=1
-for skip in 0 32 48 8 128 176; do
-  echo "### RCB_TC_DEBUG_SKIP=$skip" >> $out
-  RCB_TC_DEBUG_SKIP=$skip timeout 120 python tools/power_timeline.py --seconds 3 --what build 2>&1 | grep -E "t= 0\.0|t= 2\.[47]" >> $out
+export RCB_LIB_VARIANT=r1
+for n in 1 2 1 2; do
+  echo "### burst RCB_TC_NCTA=$n" >> $out
+  RCB_TC_NCTA=$n timeout 120 python tools/time_build.py --mode bf16x3 --reps 10 2>&1 | grep -v Warn | grep build >> $out
+done
+for n in 1 2; do
+  echo "### sustained build RCB_TC_NCTA=$n" >> $out
+  RCB_TC_NCTA=$n timeout 120 python tools/power_timeline.py --seconds 3 --what build --mode bf16x3 2>&1 | grep -E "t= 2\.[47]" >> $out
+  echo "### sustained step RCB_TC_NCTA=$n" >> $out
+  RCB_TC_NCTA=$n timeout 120 python tools/power_timeline.py --seconds 3 --what step --mode bf16x3 2>&1 | grep -E "t= 2\.[47]" >> $out
 done
 cat $out
