@@ -249,8 +249,14 @@ class CorrBlock:
         mode = _cabi.BUILD_MODES[mode or DEFAULT_MODE]
         pyr_dtype = {"f32": _cabi.F32, "f16": _cabi.F16}[pyramid_dtype]
         f1, f2 = _prep(fmap1, "fmap1"), _prep(fmap2, "fmap2")
-        self._state = _State(f1, f2, num_levels, radius, mode, pyr_dtype)
         self._token = None
+        self._empty_shape = None
+        if f1.shape[0] == 0:  # an empty batch passes through the reference's torch ops; there is nothing to launch
+            self._state = None
+            self._empty_shape = tuple(f1.shape)
+            self._empty_device = f1.device
+            return
+        self._state = _State(f1, f2, num_levels, radius, mode, pyr_dtype)
         if torch.is_grad_enabled() and (fmap1.requires_grad or fmap2.requires_grad):
             self._token = _BuildFn.apply(fmap1, fmap2, self._state)
 
@@ -264,15 +270,28 @@ class CorrBlock:
         pyr_dtype = {"f32": _cabi.F32, "f16": _cabi.F16}[pyramid_dtype]
         self._state = _State(None, None, num_levels, radius, packed.mode, pyr_dtype, packed=packed)
         self._token = None
+        self._empty_shape = None
         return self
 
     @property
     def corr_pyramid(self):
         """List of num_levels tensors [N*H*W, 1, H_i, W_i] like the reference attribute (core/corr.py:38,46-54);
         nothing outside corr.py reads it in the reference.  Materialised on access from the tiled buffers."""
+        if self._state is None:
+            _, _, H, W = self._empty_shape
+            return [torch.empty((0, 1, H >> l, W >> l), dtype=torch.float32, device=self._empty_device)
+                    for l in range(self.num_levels)]
         return self._state.pyr.views()
 
+    def _empty_out(self, coords, channels):
+        _, _, H, W = self._empty_shape
+        if tuple(coords.shape) != (0, 2, H, W):
+            raise RuntimeError(f"coords shape {tuple(coords.shape)} does not match the feature maps")
+        return torch.empty((0, channels, H, W), dtype=torch.float32, device=coords.device)
+
     def __call__(self, coords):
+        if self._state is None:
+            return self._empty_out(coords, self.num_levels * (2 * self.radius + 1) ** 2)
         if torch.is_grad_enabled() and (self._token is not None or coords.requires_grad):
             return _LookupFn.apply(coords, self._token, self._state)
         return self._state.lookup(_prep(coords, "coords"))
@@ -282,6 +301,8 @@ class CorrBlock:
         materialising the correlation tensor; ``packed`` is a PackedConvC1.  Inference only (no autograd), fp32
         pyramids; fp16 tensor-core operands with fp32 accumulation.  Returns [N, cout, H, W] fp32."""
         st = self._state
+        if st is None:
+            return self._empty_out(coords, packed.cout)
         if st.pyr.dtype != _cabi.F32:
             raise RuntimeError("lookup_conv needs an fp32 pyramid")
         if (packed.num_levels, packed.radius) != (self.num_levels, self.radius):
@@ -303,6 +324,8 @@ class CorrBlock:
         """[N,C,H,W] x2 -> [N,H,W,1,H,W] = fmap1^T fmap2 / sqrt(C) (reference core/corr.py:96-127)."""
         f1, f2 = _prep(fmap1, "fmap1"), _prep(fmap2, "fmap2")
         B, C, H, W = f1.shape
+        if B == 0:
+            return torch.empty((0, H, W, 1, H, W), dtype=torch.float32, device=f1.device)
         pyr = _Pyramid(B, H, W, 1, f1.device)
         _build(f1, f2, 1, _cabi.BUILD_MODES[mode or DEFAULT_MODE], pyr)
         return pyr.level(0).reshape(B, H, W, 1, H, W)
@@ -399,6 +422,10 @@ class AlternateCorrBlock:
         B, C, H, W = f1.shape
         self._shape = (B, C, H, W)
         self._src = (f1, f2)
+        self._token = None
+        if B == 0:  # empty batch: nothing to prepare, calls return empty tensors
+            self._f1n, self._f2n = None, []
+            return
         self._f1n = torch.empty((B, H, W, C), dtype=torch.float32, device=f1.device)
         self._f2n = []
         h, w = H, W
@@ -425,6 +452,12 @@ class AlternateCorrBlock:
         pyramid[0][0] and pyramid[i][1] are ever used (core/corr.py:183-184); fmap2 entries are views of the
         NHWC buffers the kernels read, the unused pooled fmap1 entries are materialised on demand."""
         f1, f2 = self._src
+        if self._shape[0] == 0:  # empty batch: plain pooled (empty) tensors
+            out = [(f1, f2)]
+            for _ in range(self.num_levels):
+                f1, f2 = F.avg_pool2d(f1, 2, stride=2), F.avg_pool2d(f2, 2, stride=2)
+                out.append((f1, f2))
+            return out
         out = [(f1, self._f2n[0].permute(0, 3, 1, 2))]
         for i in range(1, self.num_levels + 1):
             f1 = F.avg_pool2d(f1, 2, stride=2)
@@ -433,6 +466,8 @@ class AlternateCorrBlock:
         return out
 
     def __call__(self, coords):
+        if self._shape[0] == 0:
+            return self._forward(coords)
         if torch.is_grad_enabled() and (self._token is not None or coords.requires_grad):
             return _AltLookupFn.apply(coords, self._token, self)
         return self._forward(_prep(coords, "coords"))
@@ -443,6 +478,8 @@ class AlternateCorrBlock:
             raise RuntimeError(f"coords shape {tuple(c.shape)} does not match the feature maps")
         rd = 2 * self.radius + 1
         out = torch.empty((B, self.num_levels * rd * rd, H, W), dtype=torch.float32, device=c.device)
+        if B == 0:
+            return out
         with torch.cuda.device(c.device):
             _cabi.check(_cabi.lib().rcb_altcorr_pyramid_forward(
                 self._f1n.data_ptr(), self._f2ptrs, c.data_ptr(), out.data_ptr(), B, C, H, W, self.num_levels,

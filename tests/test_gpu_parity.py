@@ -358,6 +358,23 @@ def test_largest_config_offsets_beyond_32_bits(rcb, dev, mode):
 # ---------------------------------------------------------------------------------------------
 # boundary behaviour
 # ---------------------------------------------------------------------------------------------
+def test_empty_batch_passes_through(rcb, dev):
+    """N = 0 goes through the reference's torch ops (empty matmul / pooling / grid_sample) and yields empty tensors of
+    the right shape; so it does here, without a launch."""
+    f = torch.empty((0, 32, 12, 16), device=dev)
+    c = torch.empty((0, 2, 12, 16), device=dev)
+    blk = rcb.CorrBlock(f, f, num_levels=3, radius=2)
+    assert tuple(blk(c).shape) == (0, 3 * 25, 12, 16)
+    assert [tuple(p.shape) for p in blk.corr_pyramid] == [(0, 1, 12, 16), (0, 1, 6, 8), (0, 1, 3, 4)]
+    assert tuple(rcb.CorrBlock.corr(f, f).shape) == (0, 12, 16, 1, 12, 16)
+    alt = rcb.AlternateCorrBlock(f, f, num_levels=3, radius=2)
+    assert tuple(alt(c).shape) == (0, 3 * 25, 12, 16)
+    assert len(alt.pyramid) == 4
+    with pytest.raises(RuntimeError):
+        blk(torch.empty((1, 2, 12, 16), device=dev))
+    torch.cuda.synchronize()
+
+
 def test_error_behaviour_matches_reference_extension(rcb, dev):
     f = torch.zeros(1, 8, 8, 16, device=dev)
     c = torch.zeros(1, 1, 8, 8, 2, device=dev)
