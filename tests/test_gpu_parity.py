@@ -358,6 +358,36 @@ def test_largest_config_offsets_beyond_32_bits(rcb, dev, mode):
 # ---------------------------------------------------------------------------------------------
 # boundary behaviour
 # ---------------------------------------------------------------------------------------------
+def test_non_finite_coordinates_and_single_pixel_levels(rcb, dev, orc):
+    """NaN / inf coordinates give zeros (the window is clamped far outside the plane), never NaN or a fault; a level
+    that is a single pixel (8 x 8 maps, 4 levels: 8, 4, 2, 1) is sampled in pixel space like every other level --
+    the reference's normalisation divides by W_i - 1 = 0 there."""
+    rs = np.random.RandomState(5)
+    B, C, H, W, L, r = 1, 16, 8, 8, 4, 4
+    f1 = rs.standard_normal((B, C, H, W)).astype(np.float32)
+    f2 = rs.standard_normal((B, C, H, W)).astype(np.float32)
+    ys, xs = np.meshgrid(np.arange(H), np.arange(W), indexing="ij")
+    coords = (np.stack([xs, ys])[None] + 1.5 * rs.standard_normal((B, 2, H, W))).astype(np.float32)
+    blk = rcb.CorrBlock(t(f1, dev), t(f2, dev), num_levels=L, radius=r)
+    alt = rcb.AlternateCorrBlock(t(f1, dev), t(f2, dev), num_levels=L, radius=r)
+    want = orc.OracleCorrBlock(f1, f2, num_levels=L, radius=r)(coords, roundtrip=False)
+    assert rel_err(blk(t(coords, dev)).cpu().numpy(), want) < TOL
+    assert rel_err(alt(t(coords, dev)).cpu().numpy(), want) < TOL
+    bad = coords.copy()
+    bad[0, 0, 0, 0] = np.nan
+    bad[0, 1, 1, 1] = np.inf
+    bad[0, 0, 2, 2] = -np.inf
+    bad[0, :, 3, 3] = np.nan
+    got = blk(t(bad, dev)).cpu().numpy()
+    assert np.isfinite(got).all()
+    for (y, x) in [(0, 0), (1, 1), (2, 2), (3, 3)]:
+        assert not got[0, :, y, x].any()
+    mask = np.ones((H, W), bool)
+    for (y, x) in [(0, 0), (1, 1), (2, 2), (3, 3)]:
+        mask[y, x] = False
+    assert rel_err(got[0][:, mask], want[0][:, mask]) < TOL  # the other queries are untouched
+
+
 def test_empty_batch_passes_through(rcb, dev):
     """N = 0 goes through the reference's torch ops (empty matmul / pooling / grid_sample) and yields empty tensors of
     the right shape; so it does here, without a launch."""
