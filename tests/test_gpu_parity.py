@@ -378,14 +378,15 @@ def test_non_finite_coordinates_and_single_pixel_levels(rcb, dev, orc):
     bad[0, 1, 1, 1] = np.inf
     bad[0, 0, 2, 2] = -np.inf
     bad[0, :, 3, 3] = np.nan
-    got = blk(t(bad, dev)).cpu().numpy()
-    assert np.isfinite(got).all()
-    for (y, x) in [(0, 0), (1, 1), (2, 2), (3, 3)]:
-        assert not got[0, :, y, x].any()
     mask = np.ones((H, W), bool)
     for (y, x) in [(0, 0), (1, 1), (2, 2), (3, 3)]:
         mask[y, x] = False
-    assert rel_err(got[0][:, mask], want[0][:, mask]) < TOL  # the other queries are untouched
+    for block in (blk, alt):  # all-pairs and on-the-fly kernels clamp the same way
+        got = block(t(bad, dev)).cpu().numpy()
+        assert np.isfinite(got).all()
+        for (y, x) in [(0, 0), (1, 1), (2, 2), (3, 3)]:
+            assert not got[0, :, y, x].any()
+        assert rel_err(got[0][:, mask], want[0][:, mask]) < TOL  # the other queries are untouched
 
 
 def test_empty_batch_passes_through(rcb, dev):
